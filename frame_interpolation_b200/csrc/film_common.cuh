@@ -1,0 +1,93 @@
+// Shared device/host definitions of the FILM B200 engine.
+//
+// Activation storage ("split" format): every feature tensor is NHWC and stored as TWO
+// 16-bit planes, hi = rn16(x) and lo = rn16(x - hi).  Same bytes as fp32, but each plane
+// is directly consumable by tcgen05.mma kind::f16, and hi + lo carries 16 mantissa bits
+// (bf16) -- the 3-pass product  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  then matches an fp32
+// convolution to ~1e-5 relative (measured against the fp64 oracle).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace film {
+
+#ifdef FILM_SPLIT_FP16
+typedef __half sp_t;
+#define FILM_SPLIT_NAME "fp16x2"
+#else
+typedef __nv_bfloat16 sp_t;
+#define FILM_SPLIT_NAME "bf16x2"
+#endif
+
+constexpr float kLeaky = 0.2f;
+
+// Split activation tensor view: [B][H][W][C] per plane, C = allocated channel stride.
+struct ActView {
+  sp_t* hi;
+  sp_t* lo;
+  int B, H, W, C;
+};
+
+__device__ __forceinline__ float sp_to_float(sp_t v) {
+#ifdef FILM_SPLIT_FP16
+  return __half2float(v);
+#else
+  return __bfloat162float(v);
+#endif
+}
+__device__ __forceinline__ sp_t float_to_sp(float v) {
+#ifdef FILM_SPLIT_FP16
+  return __float2half_rn(v);
+#else
+  return __float2bfloat16_rn(v);
+#endif
+}
+
+__device__ __forceinline__ void split2(float x, sp_t& hi, sp_t& lo) {
+  hi = float_to_sp(x);
+  lo = float_to_sp(x - sp_to_float(hi));
+}
+
+// two floats -> packed hi pair / lo pair (little-endian: element 0 in the low half)
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  sp_t ah, al, bh, bl;
+  split2(a, ah, al);
+  split2(b, bh, bl);
+  hi = (uint32_t)(*reinterpret_cast<unsigned short*>(&ah)) |
+       ((uint32_t)(*reinterpret_cast<unsigned short*>(&bh)) << 16);
+  lo = (uint32_t)(*reinterpret_cast<unsigned short*>(&al)) |
+       ((uint32_t)(*reinterpret_cast<unsigned short*>(&bl)) << 16);
+}
+
+__device__ __forceinline__ float sp_bits_to_float(uint32_t bits16) {
+#ifdef FILM_SPLIT_FP16
+  unsigned short s = (unsigned short)bits16;
+  return __half2float(*reinterpret_cast<__half*>(&s));
+#else
+  return __uint_as_float(bits16 << 16);
+#endif
+}
+
+// unpack 8 consecutive channels (one uint4 per plane) into fp32: x = hi + lo
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float* v) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+  const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = sp_bits_to_float(hw[i] & 0xffffu) + sp_bits_to_float(lw[i] & 0xffffu);
+    v[2 * i + 1] = sp_bits_to_float(hw[i] >> 16) + sp_bits_to_float(lw[i] >> 16);
+  }
+}
+
+__device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
+  split_pack2(v[0], v[1], h.x, l.x);
+  split_pack2(v[2], v[3], h.y, l.y);
+  split_pack2(v[4], v[5], h.z, l.z);
+  split_pack2(v[6], v[7], h.w, l.w);
+}
+
+__device__ __forceinline__ float leaky(float x) { return x >= 0.f ? x : x * kLeaky; }
+
+}  // namespace film

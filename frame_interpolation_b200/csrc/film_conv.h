@@ -1,0 +1,62 @@
+// Convolution problem descriptor shared by the tcgen05 implicit-GEMM kernel
+// (film_conv_tc.cu) and the CUDA-core validation kernel (film_kernels.cu).
+//
+// A "problem" is one Conv2D call site of the reference graph
+// (feature_extractor.py:94-99, pyramid_flow_estimator.py:67-72, fusion.py:83-96) viewed as
+// an implicit GEMM:  M = B*H*W output-grid pixels, N = Cout, K = sum over sources, 64-channel
+// chunks and taps.  The K loop walks (source, chunk, tap) in that order; channel concats of
+// the reference (`tf.concat`, feature_extractor.py:191, pyramid_flow_estimator.py:95,
+// util.py:142, fusion.py:136) are never materialised -- each concat operand is a source.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include "film_common.cuh"
+
+namespace film {
+
+constexpr int kMaxSrc = 4;
+constexpr int kMaxTaps = 9;
+constexpr int kChunk = 64;   // channels per K block (64 x 2 B = one 128 B swizzle row)
+constexpr int kTileM = 128;  // output pixels per CTA tile (tile_h x tile_w)
+
+struct ConvSrc {
+  const sp_t* hi;
+  const sp_t* lo;
+  int C;       // channel stride of the tensor (allocated channels)
+  int c_off;   // first channel consumed
+  int nchunk;  // number of 64-channel chunks consumed
+  int pad_;
+};
+
+struct alignas(64) ConvProblem {
+  CUtensorMap tm_a_hi[kMaxSrc];
+  CUtensorMap tm_a_lo[kMaxSrc];
+  CUtensorMap tm_w_hi;
+  CUtensorMap tm_w_lo;
+  ConvSrc src[kMaxSrc];
+  int nsrc;
+  int B, H, W;              // GEMM-M grid == input grid
+  int tile_h, tile_w;       // tile_h * tile_w == 128
+  int tiles_y, tiles_x;
+  int ntaps;
+  int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+  int ktot;                 // total K (multiple of 64)
+  const sp_t* w_hi;         // [cout][ktot] K-major
+  const sp_t* w_lo;
+  const float* bias;        // [cout]
+  int cout;
+  int act;                  // 1 = LeakyReLU(0.2)
+  sp_t* out_hi;
+  sp_t* out_lo;
+  int out_C, out_c_off;     // channel stride / first channel of the destination slice
+  int out_H, out_W;         // destination spatial dims
+  int out_sy, out_sx, out_oy, out_ox;  // dest pixel = (y*sy + oy, x*sx + ox)
+};
+
+// launchers (film_conv_tc.cu / film_kernels.cu)
+cudaError_t launch_conv_tc(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
+cudaError_t launch_conv_simt(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
+cudaError_t conv_tc_configure();  // cudaFuncSetAttribute for all instantiations
+
+}  // namespace film

@@ -1,0 +1,339 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (the engine's hot kernel).
+//
+// One CTA computes a 128-pixel (tile_h x tile_w) x BN-channel output tile of one Conv2D
+// call site (film_conv.h).  GEMM view: D[128 x BN] += A[128 x 64] * W[BN x 64]^T per K block,
+// K blocks = (source, 64-channel chunk, tap).
+//
+//   warp 0    : TMA producer.  Per K block: 4-D tiled TMA loads of the hi and lo planes of the
+//               activation box (64 ch, tile_w, tile_h, 1) at the tap-shifted coordinate --
+//               out-of-bounds rows/cols are zero-filled by TMA, which IS the SAME padding of
+//               tf.keras Conv2D -- plus 2-D loads of the W_hi / W_lo [BN x 64] blocks.
+//               Everything lands in SWIZZLE_128B K-major layout (one pixel = one 128 B row).
+//   warp 1    : allocates TMEM (BN fp32 columns) and issues tcgen05.mma.kind::f16 (M=128,
+//               N=BN, K=16): per K block 4 k-steps x 3 passes  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi
+//               (split-precision product, fp32 accumulate in TMEM).  tcgen05.commit releases
+//               smem stages back to the producer and finally signals the epilogue.
+//   warps 2-5 : epilogue.  tcgen05.ld (32 lanes x 32 columns per warp), + bias, LeakyReLU,
+//               re-split to hi/lo 16-bit planes, 128-bit stores into the destination channel
+//               slice (which is how channel concats and the NN-upsample parity scatter are
+//               realised without extra passes).
+//
+// mbarrier pipeline: full[s] (TMA -> MMA, tx-count), empty[s] (MMA -> TMA, via tcgen05.commit),
+// tmem_full (MMA -> epilogue).  A watchdog turns a stuck barrier into a trap instead of a hang.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <stdint.h>
+
+#include "film_conv.h"
+
+namespace film {
+
+namespace {
+
+constexpr int kNumThreads = 192;
+constexpr int kABytes = kTileM * kChunk * 2;  // 16 KiB per plane
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kWBytes = BN * kChunk * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : (BN == 64) ? 4 : 5;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // stages + barriers (8 B each) + tmem ptr + bias
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + BN * 4;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("film conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 [32,46) = 1024 B
+// (8 rows x 128 B), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format=F32 [4,6),
+// a_format [7,10), b_format [10,13) (0 = F16, 1 = BF16), K-major A and B, N>>3 [17,23), M>>4 [24,29).
+template <int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+#ifdef FILM_SPLIT_FP16
+  constexpr uint32_t fmt = 0;
+#else
+  constexpr uint32_t fmt = 1;
+#endif
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) k_conv_tc(const ConvProblem* __restrict__ prob) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const ConvProblem& P = *prob;
+
+  // carve shared memory (1024 B alignment required by SWIZZLE_128B)
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bar_base = base + Cfg::kStages * Cfg::kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full ; then tmem ptr ; then bias
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
+  uint32_t* tmem_ptr_smem =
+      reinterpret_cast<uint32_t*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+  float* bias_smem = reinterpret_cast<float*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tx = tile % P.tiles_x;
+  tile /= P.tiles_x;
+  const int ty = tile % P.tiles_y;
+  const int b = tile / P.tiles_y;
+  const int y0 = ty * P.tile_h, x0 = tx * P.tile_w;
+  const int n0 = blockIdx.y * BN;
+
+  int nkb = 0;
+  for (int s = 0; s < P.nsrc; ++s) nkb += P.src[s].nchunk * P.ntaps;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_smem[i] = (n0 + i < P.cout) ? P.bias[n0 + i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int kb = 0;
+      for (int s = 0; s < P.nsrc; ++s) {
+        const int nchunk = P.src[s].nchunk, c_off = P.src[s].c_off;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          for (int t = 0; t < P.ntaps; ++t, ++kb) {
+            const int stage = kb % Cfg::kStages;
+            const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * Cfg::kStageBytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            const int cc = c_off + ch * kChunk, xx = x0 + P.tap_dx[t], yy = y0 + P.tap_dy[t];
+            tma_load_4d(sa, &P.tm_a_hi[s], full_bar(stage), cc, xx, yy, b);
+            tma_load_4d(sa + kABytes, &P.tm_a_lo[s], full_bar(stage), cc, xx, yy, b);
+            tma_load_2d(sa + 2 * kABytes, &P.tm_w_hi, full_bar(stage), kb * kChunk, n0);
+            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, &P.tm_w_lo, full_bar(stage), kb * kChunk, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<BN>();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = kb % Cfg::kStages;
+        const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kABytes);
+        const uint64_t w_hi = make_desc(sa + 2 * kABytes), w_lo = make_desc(sa + 2 * kABytes + Cfg::kWBytes);
+#pragma unroll
+        for (int k = 0; k < kChunk / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 elements x 2 B = 32 B along K
+          umma(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma(tmem_base, a_hi + adv, w_lo + adv, idesc, 1u);
+          umma(tmem_base, a_hi + adv, w_hi + adv, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row == TMEM lane
+    const int py = y0 + r / P.tile_w, px = x0 + r % P.tile_w;
+    const bool valid = (py < P.H) && (px < P.W);
+    const int64_t opix =
+        ((int64_t)b * P.out_H + ((int64_t)py * P.out_sy + P.out_oy)) * P.out_W + ((int64_t)px * P.out_sx + P.out_ox);
+    sp_t* oh = P.out_hi + opix * P.out_C + P.out_c_off + n0;
+    sp_t* ol = P.out_lo + opix * P.out_C + P.out_c_off + n0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      if (n0 + cc * 32 >= P.cout) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = __uint_as_float(v[g * 8 + j]) + bias_smem[cc * 32 + g * 8 + j];
+            f[j] = P.act ? leaky(x) : x;
+          }
+          uint4 h, l;
+          pack8(f, h, l);
+          *reinterpret_cast<uint4*>(oh + cc * 32 + g * 8) = h;
+          *reinterpret_cast<uint4*>(ol + cc * 32 + g * 8) = l;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+template <int BN>
+cudaError_t launch_bn(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
+  dim3 grid(h.B * h.tiles_y * h.tiles_x, (h.cout + BN - 1) / BN);
+  k_conv_tc<BN><<<grid, kNumThreads, TcCfg<BN>::kSmemBytes, st>>>(d_prob);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int conv_tc_block_n(int cout) { return cout >= 256 ? 256 : cout >= 128 ? 128 : cout >= 64 ? 64 : 32; }
+
+cudaError_t conv_tc_configure() {
+  cudaError_t e;
+#define FILM_CFG(BN)                                                                             \
+  e = cudaFuncSetAttribute(k_conv_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                           TcCfg<BN>::kSmemBytes);                                               \
+  if (e != cudaSuccess) return e;
+  FILM_CFG(32) FILM_CFG(64) FILM_CFG(128) FILM_CFG(256)
+#undef FILM_CFG
+  return cudaSuccess;
+}
+
+cudaError_t launch_conv_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
+  switch (conv_tc_block_n(h.cout)) {
+    case 256: return launch_bn<256>(d_prob, h, st);
+    case 128: return launch_bn<128>(d_prob, h, st);
+    case 64: return launch_bn<64>(d_prob, h, st);
+    default: return launch_bn<32>(d_prob, h, st);
+  }
+}
+
+}  // namespace film

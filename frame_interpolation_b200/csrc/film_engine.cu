@@ -1,0 +1,1073 @@
+// Host side of the FILM B200 engine: weight loading + repacking, per-shape execution plans
+// (arena, TMA tensor maps, static kernel schedule captured in a CUDA graph) and the C ABI of
+// include/film_b200.h.  Network wiring follows the reference graph,
+// models/film_net/interpolator.py:120-207; each step cites the lines it replaces.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/film_b200.h"
+#include "film_conv.h"
+#include "film_kernels.h"
+
+namespace film {
+int conv_tc_block_n(int cout);
+
+// ----------------------------------------------------------------------------------------
+// architecture constants (training/config/film_net-Style.gin:17-23)
+// ----------------------------------------------------------------------------------------
+constexpr int kLevels = 7, kFusionLevels = 5, kSpecialized = 3, kSubLevels = 4, kFilters = 64;
+static const int kFlowFilters[4] = {32, 64, 128, 256};
+static const char* kPredictorNames[4] = {"flow_predictor_0", "flow_predictor_1", "flow_predictor_2",
+                                         "flow_predictor_shared"};
+static int feat_channels(int l) {
+  int c = 0;
+  for (int j = 0; j <= (l < kSubLevels - 1 ? l : kSubLevels - 1); ++j) c += kFilters << j;
+  return c;
+}
+static int fusion_filters(int l) { return l < kSpecialized ? (kFilters << l) : (kFilters << kSpecialized); }
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Error {
+  int code;
+  std::string msg;
+};
+#define FILM_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      throw Error{FILM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)};        \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------
+// weight file (FILMW1, frame_interpolation_b200/weights.py)
+// ----------------------------------------------------------------------------------------
+struct HostTensor {
+  std::vector<int> dims;
+  std::vector<float> data;
+};
+typedef std::map<std::string, HostTensor> WeightMap;
+
+static WeightMap read_weight_file(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) throw Error{FILM_ERR_WEIGHTS, std::string("cannot open weight file ") + path};
+  WeightMap m;
+  auto fail = [&](const char* why) {
+    fclose(f);
+    throw Error{FILM_ERR_WEIGHTS, std::string(path) + ": " + why};
+  };
+  char magic[8];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "FILMW1\0\0", 8) != 0) fail("bad magic");
+  uint32_t n;
+  if (fread(&n, 4, 1, f) != 1) fail("truncated");
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t ln, nd;
+    if (fread(&ln, 4, 1, f) != 1 || ln > 4096) fail("bad name length");
+    std::string name(ln, '\0');
+    if (fread(&name[0], 1, ln, f) != ln) fail("truncated");
+    if (fread(&nd, 4, 1, f) != 1 || nd > 8) fail("bad rank");
+    HostTensor t;
+    size_t cnt = 1;
+    for (uint32_t d = 0; d < nd; ++d) {
+      uint32_t v;
+      if (fread(&v, 4, 1, f) != 1) fail("truncated");
+      t.dims.push_back((int)v);
+      cnt *= v;
+    }
+    t.data.resize(cnt);
+    if (fread(t.data.data(), 4, cnt, f) != cnt) fail("truncated tensor data");
+    m[name] = std::move(t);
+  }
+  fclose(f);
+  return m;
+}
+
+static const HostTensor& get_tensor(const WeightMap& m, const std::string& name, std::vector<int> dims) {
+  auto it = m.find(name);
+  if (it == m.end()) throw Error{FILM_ERR_WEIGHTS, "missing tensor " + name};
+  if (it->second.dims != dims) throw Error{FILM_ERR_WEIGHTS, "shape mismatch for " + name};
+  return it->second;
+}
+
+// ----------------------------------------------------------------------------------------
+// host-side rounding to the 16-bit split format (round-to-nearest-even, like the device)
+// ----------------------------------------------------------------------------------------
+static uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static uint16_t f32_to_sp(float f) {
+#ifdef FILM_SPLIT_FP16
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+#else
+  return f32_to_bf16(f);
+#endif
+}
+static float sp_to_f32(uint16_t h) {
+#ifdef FILM_SPLIT_FP16
+  __half v;
+  memcpy(&v, &h, 2);
+  return __half2float(v);
+#else
+  return bf16_to_f32(h);
+#endif
+}
+
+// ----------------------------------------------------------------------------------------
+// packed weights of one tensor-core conv call-site type
+// ----------------------------------------------------------------------------------------
+struct PackedConv {
+  sp_t* w_hi = nullptr;
+  sp_t* w_lo = nullptr;
+  float* bias = nullptr;
+  int cout = 0, ktot = 0;
+  std::vector<int> src_chunks;  // 64-channel chunks per source
+  int ntaps = 0;
+  int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+};
+
+struct TapSpec {
+  int dy, dx;                               // offset on the input grid
+  std::vector<std::pair<int, int>> terms;   // kernel positions (ky,kx) summed into this tap
+};
+
+// kernel: HWIO [kh][kw][cin][cout].  src_maps[s][slot] = reference input channel or -1 (zero).
+// K order = (source, 64-chunk, tap, channel-in-chunk), matching the kernels' K loop.
+static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
+                            const std::vector<std::vector<int>>& src_maps,
+                            const std::vector<TapSpec>& taps, std::vector<void*>& allocs) {
+  const int kw = kernel.dims[1], cin = kernel.dims[2], cout = kernel.dims[3];
+  PackedConv pc;
+  pc.cout = cout;
+  pc.ntaps = (int)taps.size();
+  for (size_t t = 0; t < taps.size(); ++t) {
+    pc.tap_dy[t] = taps[t].dy;
+    pc.tap_dx[t] = taps[t].dx;
+  }
+  int ktot = 0;
+  for (auto& sm : src_maps) {
+    if (sm.size() % kChunk) throw Error{FILM_ERR_WEIGHTS, "source channel map not a multiple of 64"};
+    pc.src_chunks.push_back((int)sm.size() / kChunk);
+    ktot += (int)sm.size() * (int)taps.size();
+  }
+  pc.ktot = ktot;
+  std::vector<uint16_t> hi((size_t)cout * ktot), lo((size_t)cout * ktot);
+  int kbase = 0;
+  for (auto& sm : src_maps) {
+    const int nchunk = (int)sm.size() / kChunk;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      for (size_t t = 0; t < taps.size(); ++t, kbase += kChunk) {
+        for (int c = 0; c < kChunk; ++c) {
+          const int ref = sm[ch * kChunk + c];
+          for (int n = 0; n < cout; ++n) {
+            float w = 0.f;
+            if (ref >= 0) {
+              if (ref >= cin) throw Error{FILM_ERR_WEIGHTS, "channel map out of range"};
+              for (auto& term : taps[t].terms)
+                w += kernel.data[(((size_t)term.first * kw + term.second) * cin + ref) * cout + n];
+            }
+            const uint16_t h = f32_to_sp(w);
+            const uint16_t l = f32_to_sp(w - sp_to_f32(h));
+            hi[(size_t)n * ktot + kbase + c] = h;
+            lo[(size_t)n * ktot + kbase + c] = l;
+          }
+        }
+      }
+    }
+  }
+  FILM_CUDA(cudaMalloc(&pc.w_hi, hi.size() * 2));
+  allocs.push_back(pc.w_hi);
+  FILM_CUDA(cudaMalloc(&pc.w_lo, lo.size() * 2));
+  allocs.push_back(pc.w_lo);
+  FILM_CUDA(cudaMalloc(&pc.bias, cout * 4));
+  allocs.push_back(pc.bias);
+  FILM_CUDA(cudaMemcpy(pc.w_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+  FILM_CUDA(cudaMemcpy(pc.w_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  FILM_CUDA(cudaMemcpy(pc.bias, bias.data.data(), cout * 4, cudaMemcpyHostToDevice));
+  return pc;
+}
+
+static std::vector<TapSpec> taps_3x3() {
+  std::vector<TapSpec> t;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) t.push_back({ky - 1, kx - 1, {{ky, kx}}});
+  return t;
+}
+// fusion.py:133-135: NN 2x upsample followed by a 2x2 SAME conv (pad bottom/right), evaluated on
+// the COARSE grid per output parity (py,px): fine tap (fy,fx) reads coarse offset ((py+fy)/2,
+// (px+fx)/2); taps that hit the same coarse pixel have their weights pre-summed.
+static std::vector<TapSpec> taps_up2x2(int py, int px) {
+  std::vector<TapSpec> t;
+  for (int dy = 0; dy <= py; ++dy)
+    for (int dx = 0; dx <= px; ++dx) {
+      TapSpec s{dy, dx, {}};
+      for (int fy = 0; fy < 2; ++fy)
+        for (int fx = 0; fx < 2; ++fx)
+          if ((py + fy) / 2 == dy && (px + fx) / 2 == dx) s.terms.push_back({fy, fx});
+      t.push_back(s);
+    }
+  return t;
+}
+static std::vector<int> iota_map(int start, int n, int padded) {
+  std::vector<int> m(padded, -1);
+  for (int i = 0; i < n; ++i) m[i] = start + i;
+  return m;
+}
+// side tensor slots (film_kernels.h launch_fusion_side) -> channels of the reference's aligned
+// pyramid [img0w(3), feat0w(C), img1w(3), feat1w(C), bwd(2), fwd(2)] (interpolator.py:167-183)
+static std::vector<int> side_map(int C) {
+  std::vector<int> m(kChunk, -1);
+  for (int c = 0; c < 3; ++c) m[c] = c;
+  for (int c = 0; c < 3; ++c) m[3 + c] = 3 + C + c;
+  m[6] = 6 + 2 * C;
+  m[7] = 7 + 2 * C;
+  m[8] = 8 + 2 * C;
+  m[9] = 9 + 2 * C;
+  return m;
+}
+
+// ----------------------------------------------------------------------------------------
+// model weights on the device
+// ----------------------------------------------------------------------------------------
+struct Model {
+  std::vector<void*> allocs;
+  float *conv0_w = nullptr, *conv0_b = nullptr;  // cfeat_conv_0 [27][64]
+  PackedConv fe[8];                              // fe[1..7]
+  PackedConv flow[4][3];                         // predictor p, 3x3 conv k
+  float *flow_w3[4], *flow_b3[4], *flow_w4[4], *flow_b4[4];
+  PackedConv fus_up[4][4];                       // level i, parity class py*2+px
+  PackedConv fus_c1[4], fus_c2[4];
+  float *rgb_w = nullptr, *rgb_b = nullptr;
+
+  float* upload(const HostTensor& t) {
+    float* d;
+    FILM_CUDA(cudaMalloc(&d, t.data.size() * 4));
+    allocs.push_back(d);
+    FILM_CUDA(cudaMemcpy(d, t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice));
+    return d;
+  }
+
+  void load(const WeightMap& w) {
+    const std::string fe_pre = "feat_net/sub_extractor/cfeat_conv_";
+    conv0_w = upload(get_tensor(w, fe_pre + "0/kernel", {3, 3, 3, 64}));
+    conv0_b = upload(get_tensor(w, fe_pre + "0/bias", {64}));
+    int cin = 64;
+    for (int k = 1; k < 8; ++k) {
+      const int c = kFilters << (k / 2);
+      fe[k] = pack_conv(get_tensor(w, fe_pre + std::to_string(k) + "/kernel", {3, 3, cin, c}),
+                        get_tensor(w, fe_pre + std::to_string(k) + "/bias", {c}),
+                        {iota_map(0, cin, cin)}, taps_3x3(), allocs);
+      cin = c;
+    }
+    for (int p = 0; p < 4; ++p) {
+      const std::string pre = std::string("predict_flow/") + kPredictorNames[p] + "/conv_";
+      const int nf = kFlowFilters[p], C = feat_channels(p);
+      flow[p][0] = pack_conv(get_tensor(w, pre + "0/kernel", {3, 3, 2 * C, nf}),
+                             get_tensor(w, pre + "0/bias", {nf}),
+                             {iota_map(0, C, C), iota_map(C, C, C)}, taps_3x3(), allocs);
+      for (int k = 1; k < 3; ++k)
+        flow[p][k] = pack_conv(get_tensor(w, pre + std::to_string(k) + "/kernel", {3, 3, nf, nf}),
+                               get_tensor(w, pre + std::to_string(k) + "/bias", {nf}),
+                               {iota_map(0, nf, round_up(nf, kChunk))}, taps_3x3(), allocs);
+      flow_w3[p] = upload(get_tensor(w, pre + "3/kernel", {1, 1, nf, nf / 2}));
+      flow_b3[p] = upload(get_tensor(w, pre + "3/bias", {nf / 2}));
+      flow_w4[p] = upload(get_tensor(w, pre + "4/kernel", {1, 1, nf / 2, 2}));
+      flow_b4[p] = upload(get_tensor(w, pre + "4/bias", {2}));
+    }
+    for (int i = 0; i < kFusionLevels - 1; ++i) {
+      const std::string pre = "fusion/level_" + std::to_string(i) + "/conv_";
+      const int nf = fusion_filters(i), C = feat_channels(i);
+      const bool from_pyr = (i == kFusionLevels - 2);
+      const int Cc = feat_channels(i + 1);
+      const int coarse_c = from_pyr ? 2 * (3 + Cc) + 4 : fusion_filters(i + 1);
+      const HostTensor& k0 = get_tensor(w, pre + "0/kernel", {2, 2, coarse_c, nf});
+      const HostTensor& b0 = get_tensor(w, pre + "0/bias", {nf});
+      std::vector<std::vector<int>> up_src;
+      if (from_pyr)
+        up_src = {iota_map(3, Cc, Cc), iota_map(6 + Cc, Cc, Cc), side_map(Cc)};
+      else
+        up_src = {iota_map(0, coarse_c, coarse_c)};
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          fus_up[i][py * 2 + px] = pack_conv(k0, b0, up_src, taps_up2x2(py, px), allocs);
+      const int a_c = 2 * (3 + C) + 4;
+      fus_c1[i] = pack_conv(get_tensor(w, pre + "1/kernel", {3, 3, a_c + nf, nf}),
+                            get_tensor(w, pre + "1/bias", {nf}),
+                            {iota_map(3, C, C), iota_map(6 + C, C, C), side_map(C),
+                             iota_map(a_c, nf, round_up(nf, kChunk))},
+                            taps_3x3(), allocs);
+      fus_c2[i] = pack_conv(get_tensor(w, pre + "2/kernel", {3, 3, nf, nf}),
+                            get_tensor(w, pre + "2/bias", {nf}),
+                            {iota_map(0, nf, round_up(nf, kChunk))}, taps_3x3(), allocs);
+    }
+    rgb_w = upload(get_tensor(w, "fusion/output_conv/kernel", {1, 1, 64, 3}));
+    rgb_b = upload(get_tensor(w, "fusion/output_conv/bias", {3}));
+  }
+  ~Model() {
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched through the runtime: no -lcuda link)
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FILM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p)
+      throw Error{FILM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"};
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+#ifdef FILM_SPLIT_FP16
+static const CUtensorMapDataType kTmType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+static const CUtensorMapDataType kTmType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#endif
+
+static void make_act_map(CUtensorMap* tm, const sp_t* base, int B, int H, int W, int C, int th, int tw) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_fn()(tm, kTmType, 4, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error{FILM_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)};
+}
+static void make_w_map(CUtensorMap* tm, const sp_t* base, int cout, int ktot, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(tm, kTmType, 2, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error{FILM_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)};
+}
+
+// ----------------------------------------------------------------------------------------
+// execution plan for one (h, w, align) shape
+// ----------------------------------------------------------------------------------------
+struct SplitBuf {
+  sp_t* hi = nullptr;
+  sp_t* lo = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  int64_t pixels() const { return (int64_t)B * H * W; }
+};
+struct SrcRef {
+  const SplitBuf* buf;
+  int c_off;
+};
+struct DebugTensor {
+  bool split;
+  const void* p0;
+  const void* p1;
+  int64_t npix;
+  int C, c_off, Cn;
+};
+
+struct Plan {
+  int h, w, H, W, off_y, off_x;
+  int conv_impl;
+  std::vector<void*> allocs;
+  int64_t arena_bytes = 0;
+  std::vector<ConvProblem> h_probs;
+  ConvProblem* d_probs = nullptr;
+  std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
+  std::map<std::string, DebugTensor> debug;
+  float* xin = nullptr;   // [2][h][w][3] unpadded inputs
+  float* xout = nullptr;  // [h][w][3]
+  cudaGraphExec_t graph = nullptr;
+  double conv_flops = 0, mma_flops = 0, warp_bytes = 0;
+
+  template <class T>
+  T* alloc(int64_t count) {
+    void* p;
+    const int64_t bytes = count * (int64_t)sizeof(T);
+    FILM_CUDA(cudaMalloc(&p, bytes > 0 ? bytes : 16));
+    FILM_CUDA(cudaMemset(p, 0, bytes > 0 ? bytes : 16));
+    allocs.push_back(p);
+    arena_bytes += bytes;
+    return (T*)p;
+  }
+  SplitBuf* split(int B, int H_, int W_, int C) {
+    bufs.emplace_back(new SplitBuf);
+    SplitBuf* s = bufs.back().get();
+    s->B = B;
+    s->H = H_;
+    s->W = W_;
+    s->C = C;
+    s->hi = alloc<sp_t>((int64_t)B * H_ * W_ * C);
+    s->lo = alloc<sp_t>((int64_t)B * H_ * W_ * C);
+    return s;
+  }
+  std::vector<std::unique_ptr<SplitBuf>> bufs;
+
+  ~Plan() {
+    if (graph) cudaGraphExecDestroy(graph);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+static void pick_tile(int H, int W, int& th, int& tw) {
+  static const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+  long best = -1;
+  for (auto& c : cand) {
+    long tiles = (long)((H + c[0] - 1) / c[0]) * ((W + c[1] - 1) / c[1]);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      th = c[0];
+      tw = c[1];
+    }
+  }
+}
+
+// Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
+static void add_conv(Plan& P, const PackedConv& pc, const std::vector<SrcRef>& sources, int act,
+                     const SplitBuf* out, int out_c_off, int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
+  ConvProblem cp;
+  memset(&cp, 0, sizeof(cp));
+  const SplitBuf* s0 = sources[0].buf;
+  cp.nsrc = (int)sources.size();
+  if (cp.nsrc != (int)pc.src_chunks.size()) throw Error{FILM_ERR_WEIGHTS, "source count mismatch"};
+  cp.B = s0->B;
+  cp.H = s0->H;
+  cp.W = s0->W;
+  pick_tile(cp.H, cp.W, cp.tile_h, cp.tile_w);
+  cp.tiles_y = (cp.H + cp.tile_h - 1) / cp.tile_h;
+  cp.tiles_x = (cp.W + cp.tile_w - 1) / cp.tile_w;
+  for (int s = 0; s < cp.nsrc; ++s) {
+    const SplitBuf* b = sources[s].buf;
+    if (b->B != cp.B || b->H != cp.H || b->W != cp.W) throw Error{FILM_ERR_ARG, "conv source grid mismatch"};
+    cp.src[s].hi = b->hi;
+    cp.src[s].lo = b->lo;
+    cp.src[s].C = b->C;
+    cp.src[s].c_off = sources[s].c_off;
+    cp.src[s].nchunk = pc.src_chunks[s];
+    if (sources[s].c_off + pc.src_chunks[s] * kChunk > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
+    make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, cp.tile_h, cp.tile_w);
+    make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, cp.tile_h, cp.tile_w);
+  }
+  cp.ntaps = pc.ntaps;
+  for (int t = 0; t < pc.ntaps; ++t) {
+    cp.tap_dy[t] = pc.tap_dy[t];
+    cp.tap_dx[t] = pc.tap_dx[t];
+  }
+  cp.ktot = pc.ktot;
+  cp.w_hi = pc.w_hi;
+  cp.w_lo = pc.w_lo;
+  cp.bias = pc.bias;
+  cp.cout = pc.cout;
+  cp.act = act;
+  const int bn = conv_tc_block_n(pc.cout);
+  make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn);
+  make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn);
+  cp.out_hi = out->hi;
+  cp.out_lo = out->lo;
+  cp.out_C = out->C;
+  cp.out_c_off = out_c_off;
+  cp.out_H = out->H;
+  cp.out_W = out->W;
+  cp.out_sy = sy;
+  cp.out_sx = sx;
+  cp.out_oy = oy;
+  cp.out_ox = ox;
+  if (out->B != cp.B || out_c_off + pc.cout > out->C) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
+  const size_t idx = P.h_probs.size();
+  P.h_probs.push_back(cp);
+  Plan* pp = &P;
+  const int impl = P.conv_impl;
+  P.ops.push_back([pp, idx, impl](cudaStream_t st) {
+    return impl == 1 ? launch_conv_simt(pp->d_probs + idx, pp->h_probs[idx], st)
+                     : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
+  });
+  // issued tensor-core work: 3 passes over the padded K and the padded tile grid
+  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
+                 (double)(((pc.cout + bn - 1) / bn) * bn);
+}
+
+static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug) {
+  std::unique_ptr<Plan> pl(new Plan);
+  Plan& P = *pl;
+  P.h = h;
+  P.w = w;
+  P.conv_impl = conv_impl;
+  // eval/interpolator.py:30-63
+  int ph = 0, pw = 0;
+  if (align > 0) {
+    ph = (h % align) ? align - h % align : 0;
+    pw = (w % align) ? align - w % align : 0;
+  }
+  P.H = h + ph;
+  P.W = w + pw;
+  P.off_y = ph / 2;
+  P.off_x = pw / 2;
+  if (P.H % 64 || P.W % 64)
+    throw Error{FILM_ERR_ARG, "padded frame size must be a multiple of 64 (2^(pyramid_levels-1)); use align=64"};
+  int Hs[kLevels], Ws[kLevels];
+  for (int l = 0; l < kLevels; ++l) {
+    Hs[l] = P.H >> l;
+    Ws[l] = P.W >> l;
+  }
+  if (Hs[kLevels - 2] < 2 || Ws[kLevels - 2] < 2) throw Error{FILM_ERR_ARG, "frame too small"};
+
+  P.xin = P.alloc<float>((int64_t)2 * h * w * 3);
+  P.xout = P.alloc<float>((int64_t)h * w * 3);
+  Plan* pp = &P;
+
+  // ---- image pyramids (util.py:23-45), both images batched: img[l] = [2][H_l][W_l][3]
+  float* img[kLevels];
+  for (int l = 0; l < kLevels; ++l) img[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 3);
+  for (int k = 0; k < 2; ++k) {
+    float* dst = img[0] + (int64_t)k * P.H * P.W * 3;
+    const float* src = P.xin + (int64_t)k * h * w * 3;
+    P.ops.push_back([=](cudaStream_t st) {
+      return launch_pad_image(src, (int64_t)pp->w * 3, pp->h, pp->w, dst, pp->H, pp->W, pp->off_y, pp->off_x, st);
+    });
+  }
+  for (int l = 0; l + 1 < kLevels; ++l) {
+    const float* in = img[l];
+    float* out = img[l + 1];
+    const int hh = Hs[l], ww = Ws[l];
+    P.ops.push_back([=](cudaStream_t st) { return launch_image_pool(in, out, 2, hh, ww, st); });
+  }
+
+  // ---- feature extractor (feature_extractor.py:125-193), Siamese: batch = image index
+  SplitBuf* feat[kLevels];
+  for (int l = 0; l < kLevels; ++l) feat[l] = P.split(2, Hs[l], Ws[l], feat_channels(l));
+  static const int slice_off[4] = {0, 64, 192, 448};
+  for (int i = 0; i < kLevels; ++i) {
+    const int depth = (kLevels - i) < kSubLevels ? (kLevels - i) : kSubLevels;
+    SplitBuf* pooled = nullptr;
+    for (int j = 0; j < depth; ++j) {
+      const int r = i + j, c = kFilters << j;
+      SplitBuf* t1 = P.split(2, Hs[r], Ws[r], c);
+      if (j == 0) {
+        const float* im = img[i];
+        const int hh = Hs[r], ww = Ws[r];
+        const float *w0 = M.conv0_w, *b0 = M.conv0_b;
+        sp_t *oh = t1->hi, *ol = t1->lo;
+        P.ops.push_back([=](cudaStream_t st) { return launch_conv0_c3(im, 2, hh, ww, w0, b0, oh, ol, 64, 0, st); });
+      } else {
+        add_conv(P, M.fe[2 * j], {{pooled, 0}}, 1, t1, 0);
+      }
+      // second conv of the pair writes straight into the cascaded feature tensor slice
+      // (replaces the tf.concat at feature_extractor.py:191)
+      add_conv(P, M.fe[2 * j + 1], {{t1, 0}}, 1, feat[r], slice_off[j]);
+      if (j < depth - 1) {
+        pooled = P.split(2, Hs[r + 1], Ws[r + 1], c);
+        const SplitBuf* f = feat[r];
+        const SplitBuf* po = pooled;
+        const int so = slice_off[j];
+        P.ops.push_back([=](cudaStream_t st) {
+          return launch_act_pool(f->hi, f->lo, f->C, so, 2, f->H, f->W, c, po->hi, po->lo, po->C, st);
+        });
+      }
+    }
+  }
+  for (int l = 0; l < kLevels; ++l)
+    for (int k = 0; k < 2; ++k)
+      P.debug["feat" + std::to_string(k) + "/" + std::to_string(l)] =
+          DebugTensor{true, feat[l]->hi + (int64_t)k * Hs[l] * Ws[l] * feat[l]->C,
+                      feat[l]->lo + (int64_t)k * Hs[l] * Ws[l] * feat[l]->C, (int64_t)Hs[l] * Ws[l], feat[l]->C, 0,
+                      feat[l]->C};
+
+  // ---- pyramid flow estimator, both directions batched (pyramid_flow_estimator.py:125-163)
+  // batch d = 0: forward (a = feat of image 0, b = image 1); d = 1: backward.
+  float* v[kLevels];
+  float* res[kLevels];
+  for (int l = 0; l < kLevels; ++l) {
+    v[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
+    res[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
+  }
+  for (int l = kLevels - 1; l >= 0; --l) {
+    const int p = l < kSpecialized ? l : kSpecialized;
+    const int nf = kFlowFilters[p], C = feat_channels(l), hh = Hs[l], ww = Ws[l];
+    const SplitBuf* second;  // second operand of concat(a, b)
+    float* vup = nullptr;
+    if (l == kLevels - 1) {
+      // coarsest level: b = features of the other image, unwarped.  Built as a batch-swapped copy.
+      SplitBuf* sw = P.split(2, hh, ww, C);
+      const SplitBuf* f = feat[l];
+      const int64_t half = (int64_t)hh * ww * C * (int64_t)sizeof(sp_t);
+      P.ops.push_back([=](cudaStream_t st) {
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(sw->hi, (const char*)f->hi + half, half, cudaMemcpyDeviceToDevice, st))) return e;
+        if ((e = cudaMemcpyAsync((char*)sw->hi + half, f->hi, half, cudaMemcpyDeviceToDevice, st))) return e;
+        if ((e = cudaMemcpyAsync(sw->lo, (const char*)f->lo + half, half, cudaMemcpyDeviceToDevice, st))) return e;
+        return cudaMemcpyAsync((char*)sw->lo + half, f->lo, half, cudaMemcpyDeviceToDevice, st);
+      });
+      second = sw;
+    } else {
+      SplitBuf* warped = P.split(2, hh, ww, C);
+      vup = P.alloc<float>((int64_t)2 * hh * ww * 2);
+      const float* vprev = v[l + 1];
+      const SplitBuf* f = feat[l];
+      const int hc = Hs[l + 1], wc = Ws[l + 1];
+      float* vu = vup;
+      P.ops.push_back([=](cudaStream_t st) {
+        return launch_flow_warp(vprev, hc, wc, f->hi, f->lo, hh, ww, C, vu, warped->hi, warped->lo, st);
+      });
+      P.warp_bytes += 2.0 * hh * ww * (double)C * 8.0;
+      second = warped;
+    }
+    const int cpad = round_up(nf, kChunk);
+    SplitBuf* c0 = P.split(2, hh, ww, cpad);
+    SplitBuf* c1 = P.split(2, hh, ww, cpad);
+    SplitBuf* c2 = P.split(2, hh, ww, cpad);
+    add_conv(P, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0);
+    add_conv(P, M.flow[p][1], {{c0, 0}}, 1, c1, 0);
+    add_conv(P, M.flow[p][2], {{c1, 0}}, 1, c2, 0);
+    {
+      const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
+      float *rr = res[l], *vv = v[l];
+      const float* vu = vup;
+      const int npix = 2 * hh * ww;
+      P.ops.push_back([=](cudaStream_t st) {
+        return launch_flow_head(c2->hi, c2->lo, c2->C, nf, npix, w3, b3, w4, b4, vu, rr, vv, st);
+      });
+    }
+    const int64_t np = (int64_t)hh * ww;
+    P.debug["flow_fwd/" + std::to_string(l)] = DebugTensor{false, v[l], nullptr, np, 2, 0, 2};
+    P.debug["flow_bwd/" + std::to_string(l)] = DebugTensor{false, v[l] + np * 2, nullptr, np, 2, 0, 2};
+    P.debug["res_fwd/" + std::to_string(l)] = DebugTensor{false, res[l], nullptr, np, 2, 0, 2};
+    P.debug["res_bwd/" + std::to_string(l)] = DebugTensor{false, res[l] + np * 2, nullptr, np, 2, 0, 2};
+  }
+
+  // ---- fusion-stage warps (interpolator.py:153-183).  v[l] already equals the synthesised flow
+  // pyramid of util.py:106-117 (same arithmetic, same order), so that pass is not repeated.
+  SplitBuf* wf[kFusionLevels];
+  SplitBuf* side[kFusionLevels];
+  for (int l = 0; l < kFusionLevels; ++l) {
+    const int C = feat_channels(l), hh = Hs[l], ww = Ws[l];
+    wf[l] = P.split(2, hh, ww, C);
+    side[l] = P.split(1, hh, ww, kChunk);
+    const float* vv = v[l];
+    const float* im = img[l];
+    const SplitBuf *f = feat[l], *o = wf[l], *sd = side[l];
+    P.ops.push_back([=](cudaStream_t st) {
+      cudaError_t e = launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, st);
+      if (e) return e;
+      return launch_fusion_side(vv, im, hh, ww, sd->hi, sd->lo, sd->C, st);
+    });
+    P.warp_bytes += 2.0 * hh * ww * (double)(C + 3) * 8.0;
+    P.debug["aligned_side/" + std::to_string(l)] =
+        DebugTensor{true, sd->hi, sd->lo, (int64_t)hh * ww, sd->C, 0, 10};
+    for (int k = 0; k < 2; ++k)
+      P.debug["warped" + std::to_string(k) + "/" + std::to_string(l)] =
+          DebugTensor{true, o->hi + (int64_t)k * hh * ww * C, o->lo + (int64_t)k * hh * ww * C, (int64_t)hh * ww, C, 0, C};
+  }
+  // The fusion convs see one frame (B = 1): views of the two warped feature batches.
+  auto batch_view = [&](const SplitBuf* b, int k) {
+    P.bufs.emplace_back(new SplitBuf(*b));
+    SplitBuf* s = P.bufs.back().get();
+    s->B = 1;
+    s->hi = b->hi + (int64_t)k * b->H * b->W * b->C;
+    s->lo = b->lo + (int64_t)k * b->H * b->W * b->C;
+    return (const SplitBuf*)s;
+  };
+
+  // ---- fusion decoder (fusion.py:103-140)
+  const SplitBuf* net = nullptr;
+  for (int i = kFusionLevels - 2; i >= 0; --i) {
+    const int nf = fusion_filters(i), hh = Hs[i], ww = Ws[i];
+    const int cpad = round_up(nf, kChunk);
+    SplitBuf* up = P.split(1, hh, ww, cpad);
+    std::vector<SrcRef> up_src;
+    if (i == kFusionLevels - 2)
+      up_src = {{batch_view(wf[i + 1], 0), 0}, {batch_view(wf[i + 1], 1), 0}, {side[i + 1], 0}};
+    else
+      up_src = {{net, 0}};
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) add_conv(P, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
+    SplitBuf* f1 = P.split(1, hh, ww, cpad);
+    SplitBuf* f2 = P.split(1, hh, ww, cpad);
+    add_conv(P, M.fus_c1[i], {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0);
+    add_conv(P, M.fus_c2[i], {{f1, 0}}, 1, f2, 0);
+    net = f2;
+    P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
+    P.debug["fusion_up/" + std::to_string(i)] = DebugTensor{true, up->hi, up->lo, (int64_t)hh * ww, up->C, 0, nf};
+  }
+  {
+    const float *rw = M.rgb_w, *rb = M.rgb_b;
+    P.ops.push_back([=](cudaStream_t st) {
+      return launch_rgb_head(net->hi, net->lo, net->C, pp->H, pp->W, rw, rb, pp->xout, (int64_t)pp->w * 3, pp->off_y,
+                             pp->off_x, pp->h, pp->w, st);
+    });
+    P.debug["image"] = DebugTensor{false, P.xout, nullptr, (int64_t)h * w, 3, 0, 3};
+  }
+
+  // reference-graph conv FLOPs (frame_interpolation_b200/spec.py conv_macs)
+  {
+    double fe = 0, fl = 0, fu = 0;
+    for (int i = 0; i < kLevels; ++i) {
+      const int depth = (kLevels - i) < kSubLevels ? (kLevels - i) : kSubLevels;
+      int cin = 3;
+      for (int j = 0; j < depth; ++j) {
+        const double c = kFilters << j;
+        fe += (double)Hs[i + j] * Ws[i + j] * 9.0 * (cin * c + c * c);
+        cin = (int)c;
+      }
+    }
+    fe *= 2;
+    for (int l = 0; l < kLevels; ++l) {
+      const double nf = kFlowFilters[l < kSpecialized ? l : kSpecialized], cin = 2.0 * feat_channels(l);
+      fl += (double)Hs[l] * Ws[l] * (9 * cin * nf + 18 * nf * nf + nf * nf / 2 + nf);
+    }
+    fl *= 2;
+    for (int i = 0; i < kFusionLevels - 1; ++i) {
+      const double nf = fusion_filters(i), a_c = 2.0 * (3 + feat_channels(i)) + 4;
+      const double cc = (i == kFusionLevels - 2) ? 2.0 * (3 + feat_channels(i + 1)) + 4 : fusion_filters(i + 1);
+      fu += (double)Hs[i] * Ws[i] * (4 * cc * nf + 9 * (a_c + nf) * nf + 9 * nf * nf);
+    }
+    fu += (double)Hs[0] * Ws[0] * 64 * 3;
+    P.conv_flops = 2.0 * (fe + fl + fu);
+  }
+
+  FILM_CUDA(cudaMalloc(&P.d_probs, P.h_probs.size() * sizeof(ConvProblem)));
+  P.allocs.push_back(P.d_probs);
+  FILM_CUDA(cudaMemcpy(P.d_probs, P.h_probs.data(), P.h_probs.size() * sizeof(ConvProblem), cudaMemcpyHostToDevice));
+  (void)keep_debug;
+  return pl;
+}
+
+}  // namespace film
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace film;
+
+struct film_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::unique_ptr<Model> model;
+  std::map<std::string, std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+  std::string err;
+  int conv_impl = 0, use_graph = 1, keep_debug = 0;
+  film_profile_t prof;
+};
+
+static std::string g_create_error;
+
+static int fail(film_handle* h, const Error& e) {
+  if (h) h->err = e.msg; else g_create_error = e.msg;
+  return e.code;
+}
+
+static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
+  char key[96];
+  snprintf(key, sizeof(key), "%dx%d_a%d_i%d", hh, ww, align > 0 ? align : 0, h->conv_impl);
+  auto it = h->plans.find(key);
+  if (it != h->plans.end()) return it->second.get();
+  std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0);
+  if (h->use_graph) {
+    cudaGraph_t g = nullptr;
+    FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (auto& op : p->ops) {
+      e = op(h->stream);
+      if (e != cudaSuccess) break;
+    }
+    cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
+    if (e != cudaSuccess) throw Error{FILM_ERR_CUDA, std::string("kernel launch failed during capture: ") + cudaGetErrorString(e)};
+    FILM_CUDA(e2);
+    FILM_CUDA(cudaGraphInstantiate(&p->graph, g, 0));
+    cudaGraphDestroy(g);
+  }
+  Plan* raw = p.get();
+  h->plans[key] = std::move(p);
+  return raw;
+}
+
+// runs the network of plan P on its xin -> xout (stream-ordered, not synchronised)
+static void run_plan(film_handle* h, Plan* P, cudaStream_t st) {
+  if (P->graph && st == h->stream) {
+    FILM_CUDA(cudaGraphLaunch(P->graph, st));
+  } else {
+    for (auto& op : P->ops) FILM_CUDA(op(st));
+  }
+  h->last_plan = P;
+}
+
+extern "C" {
+
+const char* film_version(void) {
+  return "film_b200 0.1 sm_100a split=" FILM_SPLIT_NAME " mma=tcgen05.kind::f16 3-pass (hi*hi+hi*lo+lo*hi)";
+}
+
+int film_create(film_handle** out, const char* weights_path, int device_ordinal) {
+  if (!out || !weights_path) {
+    g_create_error = "null argument";
+    return FILM_ERR_ARG;
+  }
+  *out = nullptr;
+  film_handle* h = nullptr;
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw Error{FILM_ERR_CUDA, "no CUDA device: the FILM B200 engine has no CPU fallback"};
+    if (device_ordinal < 0 || device_ordinal >= ndev) throw Error{FILM_ERR_ARG, "bad device ordinal"};
+    FILM_CUDA(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    FILM_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10)
+      throw Error{FILM_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                     ", this engine is sm_100a-only (tcgen05/TMEM/TMA)"};
+    h = new film_handle;
+    h->device = device_ordinal;
+    memset(&h->prof, 0, sizeof(h->prof));
+    FILM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) FILM_CUDA(cudaEventCreate(&e));
+    FILM_CUDA(conv_tc_configure());
+    WeightMap w = read_weight_file(weights_path);
+    h->model.reset(new Model);
+    h->model->load(w);
+    *out = h;
+    return FILM_OK;
+  } catch (const Error& e) {
+    g_create_error = e.msg;
+    if (h) film_destroy(h);
+    return e.code;
+  }
+}
+
+void film_destroy(film_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->plans.clear();
+  h->model.reset();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* film_last_error(film_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int film_set_option(film_handle* h, const char* name, int value) {
+  if (!h || !name) return FILM_ERR_ARG;
+  std::string n(name);
+  if (n == "conv_impl") h->conv_impl = value;
+  else if (n == "use_graph") h->use_graph = value;
+  else if (n == "keep_debug") h->keep_debug = value;
+  else {
+    h->err = "unknown option " + n;
+    return FILM_ERR_ARG;
+  }
+  return FILM_OK;
+}
+
+int film_synchronize(film_handle* h) {
+  if (!h) return FILM_ERR_ARG;
+  try {
+    FILM_CUDA(cudaSetDevice(h->device));
+    FILM_CUDA(cudaStreamSynchronize(h->stream));
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+static void check_frame_args(const void* x0, const void* x1, const void* out, int B, int H, int W) {
+  if (!x0 || !x1 || !out) throw Error{FILM_ERR_ARG, "null frame pointer"};
+  if (B < 1 || H < 1 || W < 1) throw Error{FILM_ERR_ARG, "batch, height and width must be positive"};
+}
+
+static void fill_profile(film_handle* h, Plan* P, float ms_net, float ms_h2d, float ms_d2h) {
+  film_profile_t& p = h->prof;
+  p.last_call_ms = ms_net;
+  p.last_h2d_ms = ms_h2d;
+  p.last_d2h_ms = ms_d2h;
+  p.conv_flops = P->conv_flops;
+  p.mma_flops = P->mma_flops;
+  p.warp_bytes = P->warp_bytes;
+  p.kernel_launches = (int64_t)P->ops.size();
+  p.arena_bytes = P->arena_bytes;
+  p.padded_h = P->H;
+  p.padded_w = P->W;
+  p.used_graph = P->graph ? 1 : 0;
+}
+
+int film_interpolate(film_handle* h, const float* x0, const float* x1, const float* dt, int B, int H, int W,
+                     int align, float* out) {
+  if (!h) return FILM_ERR_ARG;
+  (void)dt;  // ignored like the reference ignores `time` (models/film_net/interpolator.py:102,163)
+  try {
+    check_frame_args(x0, x1, out, B, H, W);
+    FILM_CUDA(cudaSetDevice(h->device));
+    Plan* P = get_plan(h, H, W, align);
+    const size_t frame = (size_t)H * W * 3 * sizeof(float);
+    float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
+    for (int b = 0; b < B; ++b) {
+      FILM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+      FILM_CUDA(cudaMemcpyAsync(P->xin, (const char*)x0 + b * frame, frame, cudaMemcpyHostToDevice, h->stream));
+      FILM_CUDA(cudaMemcpyAsync((char*)P->xin + frame, (const char*)x1 + b * frame, frame, cudaMemcpyHostToDevice, h->stream));
+      FILM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+      run_plan(h, P, h->stream);
+      FILM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+      FILM_CUDA(cudaMemcpyAsync((char*)out + b * frame, P->xout, frame, cudaMemcpyDeviceToHost, h->stream));
+      FILM_CUDA(cudaEventRecord(h->ev[3], h->stream));
+      FILM_CUDA(cudaStreamSynchronize(h->stream));
+      float t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+      ms_h2d += t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[1], h->ev[2]));
+      ms_net += t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[2], h->ev[3]));
+      ms_d2h += t;
+    }
+    fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1, int B, int H, int W,
+                            int64_t in_pitch, int align, float* d_out, int64_t out_pitch, void* cuda_stream) {
+  if (!h) return FILM_ERR_ARG;
+  try {
+    check_frame_args(d_x0, d_x1, d_out, B, H, W);
+    if (in_pitch < (int64_t)W * 3 || out_pitch < (int64_t)W * 3) throw Error{FILM_ERR_ARG, "pitch smaller than a row"};
+    FILM_CUDA(cudaSetDevice(h->device));
+    Plan* P = get_plan(h, H, W, align);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const size_t row = (size_t)W * 3 * sizeof(float);
+    for (int b = 0; b < B; ++b) {
+      // stage into the plan's fixed input buffers so the captured graph stays pointer-stable
+      FILM_CUDA(cudaMemcpy2DAsync(P->xin, row, d_x0 + (int64_t)b * H * in_pitch, in_pitch * 4, row, H,
+                                  cudaMemcpyDeviceToDevice, st));
+      FILM_CUDA(cudaMemcpy2DAsync(P->xin + (int64_t)H * W * 3, row, d_x1 + (int64_t)b * H * in_pitch, in_pitch * 4, row, H,
+                                  cudaMemcpyDeviceToDevice, st));
+      if (st == h->stream) FILM_CUDA(cudaEventRecord(h->ev[1], st));
+      run_plan(h, P, st);
+      if (st == h->stream) FILM_CUDA(cudaEventRecord(h->ev[2], st));
+      FILM_CUDA(cudaMemcpy2DAsync(d_out + (int64_t)b * H * out_pitch, out_pitch * 4, P->xout, row, row, H,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+    fill_profile(h, P, -1.f, 0.f, 0.f);
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, const float* dt, int H, int W, int align,
+                           int block_h, int block_w, float* out) {
+  if (!h) return FILM_ERR_ARG;
+  (void)dt;
+  try {
+    check_frame_args(x0, x1, out, 1, H, W);
+    if (block_h < 1 || block_w < 1) throw Error{FILM_ERR_ARG, "block shape must be positive"};
+    // eval/interpolator.py:84-89
+    if (H % block_h) throw Error{FILM_ERR_ARG, "block_height=" + std::to_string(block_h) + " should evenly divide height=" + std::to_string(H) + "."};
+    if (W % block_w) throw Error{FILM_ERR_ARG, "block_width=" + std::to_string(block_w) + " should evenly divide width=" + std::to_string(W) + "."};
+    FILM_CUDA(cudaSetDevice(h->device));
+    const int ph = H / block_h, pw = W / block_w;
+    Plan* P = get_plan(h, ph, pw, align);
+    const size_t row = (size_t)pw * 3 * sizeof(float), full_row = (size_t)W * 3 * sizeof(float);
+    float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
+    // tiles are processed in row-major order (eval/interpolator.py:199-202), each padded on its own
+    for (int r = 0; r < block_h; ++r)
+      for (int c = 0; c < block_w; ++c) {
+        const size_t off = ((size_t)r * ph * W + (size_t)c * pw) * 3;
+        FILM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        FILM_CUDA(cudaMemcpy2DAsync(P->xin, row, x0 + off, full_row, row, ph, cudaMemcpyHostToDevice, h->stream));
+        FILM_CUDA(cudaMemcpy2DAsync(P->xin + (size_t)ph * pw * 3, row, x1 + off, full_row, row, ph, cudaMemcpyHostToDevice, h->stream));
+        FILM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        run_plan(h, P, h->stream);
+        FILM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        FILM_CUDA(cudaMemcpy2DAsync(out + off, full_row, P->xout, row, row, ph, cudaMemcpyDeviceToHost, h->stream));
+        FILM_CUDA(cudaEventRecord(h->ev[3], h->stream));
+        FILM_CUDA(cudaStreamSynchronize(h->stream));
+        float t;
+        FILM_CUDA(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        ms_h2d += t;
+        FILM_CUDA(cudaEventElapsedTime(&t, h->ev[1], h->ev[2]));
+        ms_net += t;
+        FILM_CUDA(cudaEventElapsedTime(&t, h->ev[2], h->ev[3]));
+        ms_d2h += t;
+      }
+    fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+int film_profile(film_handle* h, film_profile_t* out) {
+  if (!h || !out) return FILM_ERR_ARG;
+  if (h->prof.last_call_ms < 0 && h->last_plan) {
+    // device-pointer call on the handle's stream: resolve the event pair lazily
+    float t = 0;
+    if (cudaEventSynchronize(h->ev[2]) == cudaSuccess && cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess)
+      h->prof.last_call_ms = t;
+  }
+  *out = h->prof;
+  return FILM_OK;
+}
+
+int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count) {
+  if (!h || !name) return FILM_ERR_ARG;
+  try {
+    if (!h->last_plan) throw Error{FILM_ERR_ARG, "no call has been made yet"};
+    auto it = h->last_plan->debug.find(name);
+    if (it == h->last_plan->debug.end()) throw Error{FILM_ERR_ARG, std::string("unknown debug tensor ") + name};
+    const DebugTensor& d = it->second;
+    const int64_t n = d.npix * d.Cn;
+    if (count) *count = n;
+    if (!dst) return FILM_OK;
+    FILM_CUDA(cudaSetDevice(h->device));
+    FILM_CUDA(cudaStreamSynchronize(h->stream));
+    if (!d.split) {
+      FILM_CUDA(cudaMemcpy(dst, d.p0, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+      float* tmp;
+      FILM_CUDA(cudaMalloc(&tmp, n * 4));
+      cudaError_t e = launch_unsplit((const sp_t*)d.p0, (const sp_t*)d.p1, d.C, d.c_off, d.Cn, d.npix, tmp, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, n * 4, cudaMemcpyDeviceToHost);
+      cudaFree(tmp);
+      FILM_CUDA(e);
+    }
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+}  // extern "C"

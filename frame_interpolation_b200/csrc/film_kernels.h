@@ -1,0 +1,58 @@
+// Launchers of the bandwidth-bound (non-GEMM) kernels of the FILM engine.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "film_common.cuh"
+
+namespace film {
+
+// util.py:38-44 -- 2x2/2 VALID average pool of a 3-channel fp32 image batch.
+cudaError_t launch_image_pool(const float* in, float* out, int B, int H, int W, cudaStream_t st);
+
+// feature_extractor.py:119 (cfeat_conv_0: 3 -> 64, 3x3 SAME, LeakyReLU): K = 27, HBM-bound.
+// w: [27][64] fp32 (k = (ky*3+kx)*3 + ci), writes split output into a channel slice.
+cudaError_t launch_conv0_c3(const float* img, int B, int H, int W, const float* w,
+                            const float* bias, sp_t* out_hi, sp_t* out_lo, int out_C,
+                            int out_c_off, cudaStream_t st);
+
+// feature_extractor.py:138-146 -- 2x2/2 VALID average pool of a channel slice of a split tensor.
+cudaError_t launch_act_pool(const sp_t* in_hi, const sp_t* in_lo, int in_C, int in_c_off, int B,
+                            int H, int W, int Cn, sp_t* out_hi, sp_t* out_lo, int out_C,
+                            cudaStream_t st);
+
+// pyramid_flow_estimator.py:154-157 fused: v_up = resize_bilinear(2*v_prev -> HxW);
+// warped[d] = warp(feat[1-d], v_up[d]).  feat/warped are [2][H][W][C] split tensors.
+cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
+                             const sp_t* feat_lo, int H, int W, int C, float* v_up,
+                             sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st);
+
+// pyramid_flow_estimator.py:77-83,96-97 (conv_3: 1x1 nf->nf/2 LReLU, conv_4: 1x1 ->2 linear)
+// fused with :161 (v = v_residual + v).  x: [2][H][W][Cx] split (first nf channels real).
+cudaError_t launch_flow_head(const sp_t* x_hi, const sp_t* x_lo, int Cx, int nf, int npix,
+                             const float* w3, const float* b3, const float* w4, const float* b4,
+                             const float* v_up, float* residual, float* v, cudaStream_t st);
+
+// interpolator.py:163-183: flows * 0.5, warp of [image, features] pyramids.
+// warped[k] = warp(feat[k], 0.5 * v[1-k])   (k = 0: image 0 by backward flow, k = 1: image 1
+// by forward flow; v[0] = forward flow, v[1] = backward flow).
+cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
+                               int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st);
+// side tensor [1][H][W][side_C] split: ch 0-2 warp(img0, .5*bwd), 3-5 warp(img1, .5*fwd),
+// 6-7 .5*bwd, 8-9 .5*fwd, 10-15 zero.
+cudaError_t launch_fusion_side(const float* v, const float* img, int H, int W, sp_t* side_hi,
+                               sp_t* side_lo, int side_C, cudaStream_t st);
+
+// fusion.py:100-101,139 (1x1 conv 64 -> 3, linear) + crop (eval/interpolator.py:175).
+cudaError_t launch_rgb_head(const sp_t* x_hi, const sp_t* x_lo, int Cx, int H, int W,
+                            const float* w, const float* b, float* out, int64_t out_pitch,
+                            int off_y, int off_x, int out_h, int out_w, cudaStream_t st);
+
+// zero-pad copy (eval/interpolator.py:56): dst [H][W][3] <- src [h][w][3] at (off_y, off_x).
+cudaError_t launch_pad_image(const float* src, int64_t src_pitch, int h, int w, float* dst, int H,
+                             int W, int off_y, int off_x, cudaStream_t st);
+
+// debug: split tensor slice -> fp32 NHWC
+cudaError_t launch_unsplit(const sp_t* hi, const sp_t* lo, int C, int c_off, int Cn, int64_t npix,
+                           float* out, cudaStream_t st);
+
+}  // namespace film

@@ -1,0 +1,174 @@
+"""Drop-in for the reference's `eval/interpolator.py` on top of the B200 engine.
+
+Same class name, constructor arguments, methods, argument meaning and error behaviour
+as `eval.interpolator.Interpolator` (reference eval/interpolator.py:129-209):
+
+    Interpolator(model_path, align=None, block_shape=None)
+    .interpolate(x0, x1, dt) -> np.ndarray      # eval/interpolator.py:152-176
+    .__call__(x0, x1, dt)    -> np.ndarray      # eval/interpolator.py:178-209 (tiled if prod(block_shape) > 1)
+
+`model_path` names a FILMW1 weight file (frame_interpolation_b200/weights.py) instead of
+a TF2 SavedModel directory; the string "synthetic" (or "synthetic:<seed>") selects the
+seeded synthetic Style-architecture weights used by the tests and benchmarks.
+
+All arithmetic runs in libfilm_b200.so (hand-written sm_100a kernels) through the C ABI
+of include/film_b200.h. No TensorFlow, no torch, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib, weights as _weights
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def image_to_patches(image: np.ndarray, block_shape: List[int]) -> np.ndarray:
+    """eval/interpolator.py:66-99 (host-side helper kept for API parity)."""
+    block_height, block_width = block_shape
+    height, width, channel = image.shape[-3:]
+    patch_height, patch_width = height // block_height, width // block_width
+    assert height == (patch_height * block_height), \
+        'block_height=%d should evenly divide height=%d.' % (block_height, height)
+    assert width == (patch_width * block_width), \
+        'block_width=%d should evenly divide width=%d.' % (block_width, width)
+    x = np.reshape(image, (block_height, patch_height, block_width, patch_width, channel))
+    x = np.transpose(x, (0, 2, 1, 3, 4))
+    return np.ascontiguousarray(np.reshape(x, (block_height * block_width, patch_height, patch_width, channel)))
+
+
+def patches_to_image(patches: np.ndarray, block_shape: List[int]) -> np.ndarray:
+    """eval/interpolator.py:102-126."""
+    block_height, block_width = block_shape
+    patch_height, patch_width, channel = patches.shape[-3:]
+    x = np.reshape(patches, (block_height, block_width, patch_height, patch_width, channel))
+    x = np.transpose(x, (0, 2, 1, 3, 4))
+    return np.ascontiguousarray(np.reshape(x, (1, block_height * patch_height, block_width * patch_width, channel)))
+
+
+class Interpolator:
+    """A class for generating interpolated frames between two input frames (B200 engine)."""
+
+    def __init__(self, model_path: str, align: Optional[int] = None,
+                 block_shape: Optional[List[int]] = None, device: int = 0) -> None:
+        self._lib = _lib.load()
+        if model_path is None or str(model_path).startswith("synthetic"):
+            seed = 1234
+            if model_path and ":" in str(model_path):
+                seed = int(str(model_path).split(":", 1)[1])
+            model_path = _weights.ensure_synthetic_file(seed=seed)
+        self._handle = C.c_void_p()
+        st = self._lib.film_create(C.byref(self._handle), str(model_path).encode(), int(device))
+        if st != 0:
+            msg = self._lib.film_last_error(None).decode()
+            self._handle = C.c_void_p()
+            raise RuntimeError(f"film_create failed (status {st}): {msg}")
+        self._align = align or None
+        self._block_shape = block_shape or None
+        self.device = int(device)
+
+    # -- lifecycle ------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.film_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int) -> None:
+        if st == 0:
+            return
+        msg = self._lib.film_last_error(self._handle).decode()
+        if st == 1:
+            # the reference raises AssertionError from its shape / divisibility asserts
+            raise AssertionError(msg)
+        raise RuntimeError(f"film engine error (status {st}): {msg}")
+
+    @staticmethod
+    def _prep(x0, x1, dt):
+        # eval/interpolator.py:43-44
+        assert np.ndim(x0) == 4 and np.ndim(x1) == 4, "expected (batch, height, width, channels)"
+        x0 = np.ascontiguousarray(x0, dtype=np.float32)
+        x1 = np.ascontiguousarray(x1, dtype=np.float32)
+        assert x0.shape == x1.shape, "x0 and x1 must have the same shape"
+        assert x0.shape[-1] == 3, "expected 3 colour channels"
+        dt = np.ascontiguousarray(dt, dtype=np.float32).reshape(-1)
+        assert dt.shape[0] == x0.shape[0], "dt must have one entry per batch element"
+        return x0, x1, dt
+
+    # -- reference API --------------------------------------------------------------
+    def interpolate(self, x0: np.ndarray, x1: np.ndarray, dt: np.ndarray) -> np.ndarray:
+        """Generates an interpolated frame between given two batches of frames.
+
+        x0, x1: (batch, height, width, 3) float32; dt: (batch,), ignored by the network
+        exactly like the reference (models/film_net/interpolator.py:102). Returns the
+        unclipped (batch, height, width, 3) float32 mid-frame.
+        """
+        if self._align is not None:
+            assert self._align > 0, 'align must be a positive number.'
+        x0, x1, dt = self._prep(x0, x1, dt)
+        b, h, w, _ = x0.shape
+        out = np.empty_like(x0)
+        st = self._lib.film_interpolate(self._handle, _fptr(x0), _fptr(x1), _fptr(dt), b, h, w,
+                                        int(self._align or 0), _fptr(out))
+        self._check(st)
+        return out
+
+    def __call__(self, x0: np.ndarray, x1: np.ndarray, dt: np.ndarray) -> np.ndarray:
+        if self._block_shape is not None and np.prod(self._block_shape) > 1:
+            if self._align is not None:
+                assert self._align > 0, 'align must be a positive number.'
+            x0, x1, dt = self._prep(x0, x1, dt)
+            # the reference's reshape at eval/interpolator.py:97-98 is only valid for batch 1
+            assert x0.shape[0] == 1, "tiled interpolation expects batch size 1"
+            _, h, w, _ = x0.shape
+            bh, bw = int(self._block_shape[0]), int(self._block_shape[1])
+            out = np.empty_like(x0)
+            st = self._lib.film_interpolate_tiled(self._handle, _fptr(x0), _fptr(x1), _fptr(dt), h, w,
+                                                  int(self._align or 0), bh, bw, _fptr(out))
+            self._check(st)
+            return out
+        return self.interpolate(x0, x1, dt)
+
+    # -- engine extras (no reference counterpart) ------------------------------------
+    def interpolate_device(self, d_x0: int, d_x1: int, batch: int, height: int, width: int,
+                           d_out: int, in_pitch: Optional[int] = None,
+                           out_pitch: Optional[int] = None, stream: int = 0) -> None:
+        """Device-pointer path (raw addresses, e.g. torch.Tensor.data_ptr()); asynchronous."""
+        in_pitch = in_pitch or width * 3
+        out_pitch = out_pitch or width * 3
+        st = self._lib.film_interpolate_device(self._handle, C.c_void_p(d_x0), C.c_void_p(d_x1), batch,
+                                               height, width, in_pitch, int(self._align or 0),
+                                               C.c_void_p(d_out), out_pitch, C.c_void_p(stream))
+        self._check(st)
+
+    def synchronize(self) -> None:
+        self._check(self._lib.film_synchronize(self._handle))
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self._lib.film_set_option(self._handle, name.encode(), int(value)))
+
+    def profile(self) -> dict:
+        p = _lib.FilmProfile()
+        self._check(self._lib.film_profile(self._handle, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in p._fields_ if k != "reserved"}
+
+    def debug_read(self, name: str) -> np.ndarray:
+        n = C.c_int64()
+        self._check(self._lib.film_debug_read(self._handle, name.encode(), None, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        self._check(self._lib.film_debug_read(self._handle, name.encode(), _fptr(out), C.byref(n)))
+        return out
+
+    @property
+    def version(self) -> str:
+        return self._lib.film_version().decode()

@@ -1,0 +1,128 @@
+/*
+ * film_b200.h -- C ABI of the B200-native FILM inference engine (libfilm_b200.so).
+ *
+ * Drop-in boundary: every entry point replaces one piece of the reference's Python
+ * inference wrapper, `eval/interpolator.py` (google-research/frame-interpolation):
+ *
+ *   film_create            <- Interpolator.__init__  (eval/interpolator.py:135-150,
+ *                             tf.saved_model.load at :148)
+ *   film_interpolate       <- Interpolator.interpolate (eval/interpolator.py:152-176):
+ *                             _pad_to_align (:30-63) -> self._model(inputs) (:170-172,
+ *                             i.e. models/film_net/interpolator.py:89-207) -> crop (:175)
+ *   film_interpolate_tiled <- Interpolator.__call__ tiled branch
+ *                             (eval/interpolator.py:192-206; image_to_patches :66-99,
+ *                             patches_to_image :102-126)
+ *   film_interpolate_device<- same as film_interpolate with device-resident frames; no
+ *                             reference counterpart (the reference pays H2D + D2H + sync
+ *                             per call at :171,:176); used by the recursive scheduler
+ *                             (eval/util.py:62-91) and the multi-GPU shards.
+ *
+ * Plain C: pointers and sizes only, no torch / CUDA types in the signatures (a CUDA
+ * stream is passed as void*). All frames are float32, NHWC, C-contiguous, 3 channels,
+ * nominally in [0,1]; `dt` (B floats) is accepted and ignored exactly like the
+ * reference ignores `time` (models/film_net/interpolator.py:102,163). Outputs are
+ * NOT clipped (clipping happens in eval/util.py:51 on the reference side).
+ *
+ * Status codes: 0 ok; 1 bad argument (shape / alignment / divisibility);
+ * 2 CUDA error; 3 weight-file mismatch; 4 not supported. film_last_error() returns
+ * a human-readable message for the last non-zero status on that handle (or on
+ * creation, when handle is NULL).
+ *
+ * There is no CPU fallback: every entry point fails with status 2 if no sm_100
+ * device is present.
+ */
+#ifndef FILM_B200_H_
+#define FILM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FILM_API __attribute__((visibility("default")))
+#else
+#define FILM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct film_handle film_handle;
+
+enum {
+  FILM_OK = 0,
+  FILM_ERR_ARG = 1,
+  FILM_ERR_CUDA = 2,
+  FILM_ERR_WEIGHTS = 3,
+  FILM_ERR_UNSUPPORTED = 4
+};
+
+/* Per-call engine statistics (all times are device times from CUDA events). */
+typedef struct film_profile_t {
+  double last_call_ms;        /* event time of the last network call (excl. H2D/D2H)      */
+  double last_h2d_ms;         /* host->device copy time of the last host-pointer call     */
+  double last_d2h_ms;         /* device->host copy time of the last host-pointer call     */
+  double conv_flops;          /* reference-graph conv FLOPs of the last call (2*MAC)      */
+  double mma_flops;           /* tensor-core FLOPs actually issued (3 bf16 passes, padded K) */
+  double warp_bytes;          /* algorithmic bytes of the warp-gather kernels (rd+wr)      */
+  int64_t kernel_launches;    /* kernels launched (or graph nodes replayed) by the last call */
+  int64_t arena_bytes;        /* device memory held by the plan used by the last call     */
+  int32_t padded_h, padded_w; /* network resolution of the last call                       */
+  int32_t used_graph;         /* 1 if the last call replayed a CUDA graph                  */
+  int32_t reserved;
+} film_profile_t;
+
+/* Loads a FILMW1 weight file (see frame_interpolation_b200/weights.py), repacks the
+ * HWIO kernels into the engine's split-bf16 K-major layout on `device_ordinal`,
+ * creates the stream.  Replaces tf.saved_model.load (eval/interpolator.py:148). */
+FILM_API int film_create(film_handle** out, const char* weights_path, int device_ordinal);
+
+FILM_API void film_destroy(film_handle* h);
+
+/* Host pointers. x0/x1/out: B*H*W*3 floats. align <= 0 disables padding
+ * (eval/interpolator.py:149: `align or None`); then H and W must be multiples of 64.
+ * Blocks until `out` is written. */
+FILM_API int film_interpolate(film_handle* h, const float* x0, const float* x1, const float* dt,
+                     int B, int H, int W, int align, float* out);
+
+/* Host pointers, B == 1. Splits the frame into block_h x block_w non-overlapping tiles
+ * (row-major tile order), pads every tile independently to `align`, runs the network
+ * per tile, stitches. H % block_h == 0 and W % block_w == 0 or status 1. */
+FILM_API int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, const float* dt,
+                           int H, int W, int align, int block_h, int block_w, float* out);
+
+/* Device pointers (same layout), row pitches in floats (pitch >= W*3) so a tile of a
+ * larger frame can be passed as a strided view. Asynchronous on `cuda_stream`
+ * (a cudaStream_t; NULL = the handle's own stream, in which case the call returns after
+ * enqueueing; use film_synchronize). */
+FILM_API int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1,
+                            int B, int H, int W, int64_t in_pitch, int align,
+                            float* d_out, int64_t out_pitch, void* cuda_stream);
+
+FILM_API int film_synchronize(film_handle* h);
+
+/* Fills *out with statistics of the last call on this handle. */
+FILM_API int film_profile(film_handle* h, film_profile_t* out);
+
+/* Engine options, set before the first call of a given shape.
+ *   "conv_impl"   : 0 = tcgen05 implicit-GEMM kernels (default, the product path),
+ *                   1 = fp32 CUDA-core validation kernels (debug only; used by the
+ *                       tests to cross-check the tensor-core path on the device)
+ *   "use_graph"   : 1 = capture each shape's schedule in a CUDA graph (default), 0 = eager
+ *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read */
+FILM_API int film_set_option(film_handle* h, const char* name, int value);
+
+/* Debug/parity hook: copies an intermediate tensor of the LAST call to host as float32
+ * NHWC. `name` is e.g. "feat0/3" (feature pyramid of image 0, level 3), "flow_fwd/0",
+ * "flow_bwd/2", "image". Returns the element count through *count when dst == NULL. */
+FILM_API int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count);
+
+FILM_API const char* film_last_error(film_handle* h);
+
+/* Version / build info string: "film_b200 <ver> sm_100a split=bf16x2 mma=kind::f16 3-pass". */
+FILM_API const char* film_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FILM_B200_H_ */
