@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfilm_b200.so")
 EXPORTS = [
     "film_create", "film_destroy", "film_interpolate", "film_interpolate_tiled",
     "film_interpolate_device", "film_synchronize", "film_profile", "film_set_option",
-    "film_debug_read", "film_last_error", "film_version",
+    "film_debug_read", "film_op_table", "film_last_error", "film_version",
 ]
 
 
@@ -62,6 +62,8 @@ def load() -> C.CDLL:
     lib.film_set_option.restype = C.c_int
     lib.film_debug_read.argtypes = [C.c_void_p, C.c_char_p, fp, C.POINTER(C.c_int64)]
     lib.film_debug_read.restype = C.c_int
+    lib.film_op_table.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.film_op_table.restype = C.c_int
     lib.film_last_error.argtypes = [C.c_void_p]
     lib.film_last_error.restype = C.c_char_p
     lib.film_version.argtypes = []

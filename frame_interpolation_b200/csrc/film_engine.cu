@@ -141,7 +141,7 @@ struct PackedConv {
   sp_t* w_hi = nullptr;
   sp_t* w_lo = nullptr;
   float* bias = nullptr;
-  int cout = 0, ktot = 0;
+  int cout = 0, ktot = 0, cin_ref = 0;
   std::vector<int> src_chunks;  // 64-channel chunks per source
   int ntaps = 0;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
@@ -160,6 +160,7 @@ static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
   const int kw = kernel.dims[1], cin = kernel.dims[2], cout = kernel.dims[3];
   PackedConv pc;
   pc.cout = cout;
+  pc.cin_ref = cin;
   pc.ntaps = (int)taps.size();
   for (size_t t = 0; t < taps.size(); ++t) {
     pc.tap_dy[t] = taps[t].dy;
@@ -403,7 +404,19 @@ struct Plan {
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
   ConvProblem* d_probs = nullptr;
-  std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
+  struct Op {
+    std::function<cudaError_t(cudaStream_t)> fn;
+    int category;      // 0 = tcgen05 conv, 1 = warp gather, 2 = other bandwidth kernels
+    std::string name;
+    double flops;      // reference-graph FLOPs (convs) of this op
+    double bytes;      // algorithmic bytes (gathers)
+  };
+  std::vector<Op> ops;
+  std::vector<float> op_ms;  // filled by timed eager runs
+  void add_op(int category, const std::string& name, std::function<cudaError_t(cudaStream_t)> fn,
+              double flops = 0, double bytes = 0) {
+    ops.push_back(Op{std::move(fn), category, name, flops, bytes});
+  }
   std::map<std::string, DebugTensor> debug;
   float* xin = nullptr;   // [2][h][w][3] unpadded inputs
   float* xout = nullptr;  // [h][w][3]
@@ -453,8 +466,9 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 }
 
 // Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
-static void add_conv(Plan& P, const PackedConv& pc, const std::vector<SrcRef>& sources, int act,
-                     const SplitBuf* out, int out_c_off, int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
+static void add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
+                     const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
+                     int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
   const SplitBuf* s0 = sources[0].buf;
@@ -507,10 +521,10 @@ static void add_conv(Plan& P, const PackedConv& pc, const std::vector<SrcRef>& s
   P.h_probs.push_back(cp);
   Plan* pp = &P;
   const int impl = P.conv_impl;
-  P.ops.push_back([pp, idx, impl](cudaStream_t st) {
+  P.add_op(0, tag, [pp, idx, impl](cudaStream_t st) {
     return impl == 1 ? launch_conv_simt(pp->d_probs + idx, pp->h_probs[idx], st)
                      : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
-  });
+  }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W);
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
   P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
                  (double)(((pc.cout + bn - 1) / bn) * bn);
@@ -551,7 +565,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   for (int k = 0; k < 2; ++k) {
     float* dst = img[0] + (int64_t)k * P.H * P.W * 3;
     const float* src = P.xin + (int64_t)k * h * w * 3;
-    P.ops.push_back([=](cudaStream_t st) {
+    P.add_op(2, "pad_image", [=](cudaStream_t st) {
       return launch_pad_image(src, (int64_t)pp->w * 3, pp->h, pp->w, dst, pp->H, pp->W, pp->off_y, pp->off_x, st);
     });
   }
@@ -559,7 +573,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     const float* in = img[l];
     float* out = img[l + 1];
     const int hh = Hs[l], ww = Ws[l];
-    P.ops.push_back([=](cudaStream_t st) { return launch_image_pool(in, out, 2, hh, ww, st); });
+    P.add_op(2, "image_pool@L" + std::to_string(l), [=](cudaStream_t st) { return launch_image_pool(in, out, 2, hh, ww, st); });
   }
 
   // ---- feature extractor (feature_extractor.py:125-193), Siamese: batch = image index
@@ -577,19 +591,23 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         const int hh = Hs[r], ww = Ws[r];
         const float *w0 = M.conv0_w, *b0 = M.conv0_b;
         sp_t *oh = t1->hi, *ol = t1->lo;
-        P.ops.push_back([=](cudaStream_t st) { return launch_conv0_c3(im, 2, hh, ww, w0, b0, oh, ol, 64, 0, st); });
+        P.add_op(2, "fe_conv0@L" + std::to_string(r),
+                 [=](cudaStream_t st) { return launch_conv0_c3(im, 2, hh, ww, w0, b0, oh, ol, 64, 0, st); },
+                 2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 + 64) * 4.0);
       } else {
-        add_conv(P, M.fe[2 * j], {{pooled, 0}}, 1, t1, 0);
+        add_conv(P, "fe_conv" + std::to_string(2 * j) + "@L" + std::to_string(r), 9.0 * (c / 2) * c, M.fe[2 * j],
+                 {{pooled, 0}}, 1, t1, 0);
       }
       // second conv of the pair writes straight into the cascaded feature tensor slice
       // (replaces the tf.concat at feature_extractor.py:191)
-      add_conv(P, M.fe[2 * j + 1], {{t1, 0}}, 1, feat[r], slice_off[j]);
+      add_conv(P, "fe_conv" + std::to_string(2 * j + 1) + "@L" + std::to_string(r), 9.0 * c * c, M.fe[2 * j + 1],
+               {{t1, 0}}, 1, feat[r], slice_off[j]);
       if (j < depth - 1) {
         pooled = P.split(2, Hs[r + 1], Ws[r + 1], c);
         const SplitBuf* f = feat[r];
         const SplitBuf* po = pooled;
         const int so = slice_off[j];
-        P.ops.push_back([=](cudaStream_t st) {
+        P.add_op(2, "fe_pool@L" + std::to_string(r), [=](cudaStream_t st) {
           return launch_act_pool(f->hi, f->lo, f->C, so, 2, f->H, f->W, c, po->hi, po->lo, po->C, st);
         });
       }
@@ -620,7 +638,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       SplitBuf* sw = P.split(2, hh, ww, C);
       const SplitBuf* f = feat[l];
       const int64_t half = (int64_t)hh * ww * C * (int64_t)sizeof(sp_t);
-      P.ops.push_back([=](cudaStream_t st) {
+      P.add_op(2, "flow_swap@L" + std::to_string(l), [=](cudaStream_t st) {
         cudaError_t e;
         if ((e = cudaMemcpyAsync(sw->hi, (const char*)f->hi + half, half, cudaMemcpyDeviceToDevice, st))) return e;
         if ((e = cudaMemcpyAsync((char*)sw->hi + half, f->hi, half, cudaMemcpyDeviceToDevice, st))) return e;
@@ -635,9 +653,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       const SplitBuf* f = feat[l];
       const int hc = Hs[l + 1], wc = Ws[l + 1];
       float* vu = vup;
-      P.ops.push_back([=](cudaStream_t st) {
+      P.add_op(1, "flow_warp@L" + std::to_string(l), [=](cudaStream_t st) {
         return launch_flow_warp(vprev, hc, wc, f->hi, f->lo, hh, ww, C, vu, warped->hi, warped->lo, st);
-      });
+      }, 0, 2.0 * hh * ww * (double)C * 8.0);
       P.warp_bytes += 2.0 * hh * ww * (double)C * 8.0;
       second = warped;
     }
@@ -645,15 +663,16 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     SplitBuf* c0 = P.split(2, hh, ww, cpad);
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);
-    add_conv(P, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0);
-    add_conv(P, M.flow[p][1], {{c0, 0}}, 1, c1, 0);
-    add_conv(P, M.flow[p][2], {{c1, 0}}, 1, c2, 0);
+    const std::string lt = "@L" + std::to_string(l);
+    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0);
+    add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0);
+    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0);
     {
       const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
       float *rr = res[l], *vv = v[l];
       const float* vu = vup;
       const int npix = 2 * hh * ww;
-      P.ops.push_back([=](cudaStream_t st) {
+      P.add_op(2, "flow_head" + lt, [=](cudaStream_t st) {
         return launch_flow_head(c2->hi, c2->lo, c2->C, nf, npix, w3, b3, w4, b4, vu, rr, vv, st);
       });
     }
@@ -675,9 +694,10 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     const float* vv = v[l];
     const float* im = img[l];
     const SplitBuf *f = feat[l], *o = wf[l], *sd = side[l];
-    P.ops.push_back([=](cudaStream_t st) {
-      cudaError_t e = launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, st);
-      if (e) return e;
+    P.add_op(1, "fusion_warp@L" + std::to_string(l), [=](cudaStream_t st) {
+      return launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, st);
+    }, 0, 2.0 * hh * ww * (double)C * 8.0);
+    P.add_op(2, "fusion_side@L" + std::to_string(l), [=](cudaStream_t st) {
       return launch_fusion_side(vv, im, hh, ww, sd->hi, sd->lo, sd->C, st);
     });
     P.warp_bytes += 2.0 * hh * ww * (double)(C + 3) * 8.0;
@@ -709,18 +729,21 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     else
       up_src = {{net, 0}};
     for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) add_conv(P, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
+      for (int px = 0; px < 2; ++px)
+        add_conv(P, "fusion_up" + std::to_string(py * 2 + px) + "@L" + std::to_string(i),
+                 4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
     SplitBuf* f1 = P.split(1, hh, ww, cpad);
     SplitBuf* f2 = P.split(1, hh, ww, cpad);
-    add_conv(P, M.fus_c1[i], {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0);
-    add_conv(P, M.fus_c2[i], {{f1, 0}}, 1, f2, 0);
+    add_conv(P, "fusion_conv1@L" + std::to_string(i), 9.0 * M.fus_c1[i].cin_ref * nf, M.fus_c1[i],
+             {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0);
+    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0);
     net = f2;
     P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
     P.debug["fusion_up/" + std::to_string(i)] = DebugTensor{true, up->hi, up->lo, (int64_t)hh * ww, up->C, 0, nf};
   }
   {
     const float *rw = M.rgb_w, *rb = M.rgb_b;
-    P.ops.push_back([=](cudaStream_t st) {
+    P.add_op(2, "rgb_head", [=](cudaStream_t st) {
       return launch_rgb_head(net->hi, net->lo, net->C, pp->H, pp->W, rw, rb, pp->xout, (int64_t)pp->w * 3, pp->off_y,
                              pp->off_x, pp->h, pp->w, st);
     });
@@ -776,7 +799,8 @@ struct film_handle {
   std::map<std::string, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   std::string err;
-  int conv_impl = 0, use_graph = 1, keep_debug = 0;
+  int conv_impl = 0, use_graph = 1, keep_debug = 0, time_ops = 0;
+  std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
 };
 
@@ -798,7 +822,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
     for (auto& op : p->ops) {
-      e = op(h->stream);
+      e = op.fn(h->stream);
       if (e != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
@@ -814,10 +838,28 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
 
 // runs the network of plan P on its xin -> xout (stream-ordered, not synchronised)
 static void run_plan(film_handle* h, Plan* P, cudaStream_t st) {
-  if (P->graph && st == h->stream) {
+  if (P->graph && !h->time_ops) {  // a captured graph can be replayed on any stream
     FILM_CUDA(cudaGraphLaunch(P->graph, st));
   } else {
-    for (auto& op : P->ops) FILM_CUDA(op(st));
+    if (h->time_ops && st == h->stream) {
+      // timed eager run: one event pair per op (bench.py's live per-kernel roofline numbers)
+      const size_t n = P->ops.size();
+      while (h->op_events.size() < n + 1) {
+        cudaEvent_t e;
+        FILM_CUDA(cudaEventCreate(&e));
+        h->op_events.push_back(e);
+      }
+      FILM_CUDA(cudaEventRecord(h->op_events[0], st));
+      for (size_t i = 0; i < n; ++i) {
+        FILM_CUDA(P->ops[i].fn(st));
+        FILM_CUDA(cudaEventRecord(h->op_events[i + 1], st));
+      }
+      FILM_CUDA(cudaStreamSynchronize(st));
+      P->op_ms.assign(n, 0.f);
+      for (size_t i = 0; i < n; ++i) FILM_CUDA(cudaEventElapsedTime(&P->op_ms[i], h->op_events[i], h->op_events[i + 1]));
+    } else {
+      for (auto& op : P->ops) FILM_CUDA(op.fn(st));
+    }
   }
   h->last_plan = P;
 }
@@ -872,6 +914,7 @@ void film_destroy(film_handle* h) {
   h->model.reset();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->op_events) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -884,6 +927,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   if (n == "conv_impl") h->conv_impl = value;
   else if (n == "use_graph") h->use_graph = value;
   else if (n == "keep_debug") h->keep_debug = value;
+  else if (n == "time_ops") h->time_ops = value;
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;
@@ -1038,6 +1082,25 @@ int film_profile(film_handle* h, film_profile_t* out) {
       h->prof.last_call_ms = t;
   }
   *out = h->prof;
+  return FILM_OK;
+}
+
+int film_op_table(film_handle* h, char* buf, int64_t buf_size, int64_t* needed) {
+  if (!h || !h->last_plan) return FILM_ERR_ARG;
+  std::string out = "idx,category,name,ms,ref_flops,alg_bytes\n";
+  Plan* P = h->last_plan;
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof(line), "%zu,%d,%s,%.6f,%.0f,%.0f\n", i, P->ops[i].category, P->ops[i].name.c_str(),
+             i < P->op_ms.size() ? P->op_ms[i] : -1.f, P->ops[i].flops, P->ops[i].bytes);
+    out += line;
+  }
+  if (needed) *needed = (int64_t)out.size() + 1;
+  if (buf && buf_size > 0) {
+    const size_t n = out.size() < (size_t)buf_size - 1 ? out.size() : (size_t)buf_size - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
   return FILM_OK;
 }
 

@@ -169,6 +169,21 @@ class Interpolator:
         self._check(self._lib.film_debug_read(self._handle, name.encode(), _fptr(out), C.byref(n)))
         return out
 
+    def op_table(self) -> List[dict]:
+        """Per-kernel table of the last call (ms filled when option time_ops=1)."""
+        n = C.c_int64()
+        self._check(self._lib.film_op_table(self._handle, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self._lib.film_op_table(self._handle, buf, n.value, C.byref(n)))
+        rows = buf.value.decode().strip().split("\n")
+        keys = rows[0].split(",")
+        out = []
+        for r in rows[1:]:
+            v = r.split(",")
+            out.append({"idx": int(v[0]), "category": int(v[1]), "name": v[2], "ms": float(v[3]),
+                        "ref_flops": float(v[4]), "alg_bytes": float(v[5])})
+        return out
+
     @property
     def version(self) -> str:
         return self._lib.film_version().decode()

@@ -109,13 +109,21 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   1 = fp32 CUDA-core validation kernels (debug only; used by the
  *                       tests to cross-check the tensor-core path on the device)
  *   "use_graph"   : 1 = capture each shape's schedule in a CUDA graph (default), 0 = eager
- *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read */
+ *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read
+ *   "time_ops"    : 1 = run eagerly with one CUDA-event pair per kernel (see film_op_table) */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
 
 /* Debug/parity hook: copies an intermediate tensor of the LAST call to host as float32
  * NHWC. `name` is e.g. "feat0/3" (feature pyramid of image 0, level 3), "flow_fwd/0",
  * "flow_bwd/2", "image". Returns the element count through *count when dst == NULL. */
 FILM_API int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count);
+
+/* Per-op table of the plan used by the last call, as CSV text
+ * "idx,category,name,ms,ref_flops,alg_bytes" (category 0 = tcgen05 conv, 1 = warp gather,
+ * 2 = other bandwidth kernels). `ms` is filled by calls made with option "time_ops" = 1
+ * (eager run, one CUDA event pair per kernel on the launching stream), else -1.
+ * *needed receives the buffer size required. */
+FILM_API int film_op_table(film_handle* h, char* buf, int64_t buf_size, int64_t* needed);
 
 FILM_API const char* film_last_error(film_handle* h);
 
