@@ -1,0 +1,218 @@
+"""Parity tests proper: the CUDA engine (through the C ABI / Interpolator drop-in) against the
+CPU oracle and the committed golden vectors. Tolerance: north_star's max-abs <= 1e-3 on the
+fp32 output (we assert 2e-4, the engine's split-bf16 3-pass MMA measures ~5e-5)."""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from frame_interpolation_b200 import spec, synthetic, weights
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # the contract (BASELINE.json north_star)
+TIGHT = 2e-4        # what we actually hold ourselves to
+DT = np.full((1,), 0.5, np.float32)
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def engine(synthetic_weights):
+    from frame_interpolation_b200.interpolator import Interpolator
+    path, _ = synthetic_weights
+    eng = Interpolator(path, align=64)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def oracle(synthetic_weights):
+    import torch
+    from oracle.film_oracle import OracleInterpolator
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    return OracleInterpolator(synthetic_weights[1], align=64)
+
+
+def psnr(a, b):
+    return 10 * np.log10(1.0 / max(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2), 1e-30))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_engine_matches_golden_vectors(path, synthetic_weights):
+    from frame_interpolation_b200.interpolator import Interpolator
+    z = np.load(path)
+    c = dict(h=int(str(z["h"])), w=int(str(z["w"])), seed=int(str(z["seed"])), align=int(str(z["align"])),
+             block=ast.literal_eval(str(z["block"])))
+    assert weights.digest(synthetic_weights[1]) == str(z["weights_sha256"])
+    x0, x1 = synthetic.frame_pair(c["h"], c["w"], seed=c["seed"], n_waves=6)
+    eng = Interpolator(synthetic_weights[0], align=c["align"], block_shape=c["block"])
+    out = eng(x0, x1, DT)
+    assert out.dtype == np.float32 and out.shape == z["image"].shape
+    assert np.abs(out - z["image"]).max() < TIGHT
+    eng.close()
+
+
+@pytest.mark.parametrize("h,w,seed", [(64, 64, 0), (128, 192, 1), (256, 256, 2), (192, 320, 3), (100, 150, 4), (65, 129, 5)])
+def test_engine_matches_oracle(engine, oracle, h, w, seed):
+    x0, x1 = synthetic.frame_pair(h, w, seed=seed, n_waves=8)
+    out = engine(x0, x1, DT)
+    ref = oracle(x0, x1, DT)
+    err = np.abs(out.astype(np.float64) - ref).max()
+    assert out.shape == ref.shape == (1, h, w, 3)
+    assert err < TIGHT, err
+    assert psnr(out, ref) > 80.0                     # i.e. PSNR delta vs the reference << 0.01 dB
+
+
+def test_intermediate_tensors_match_oracle(engine, oracle):
+    """Stage-by-stage parity: feature pyramid, residual flows, flows, warped pyramids."""
+    x0, x1 = synthetic.frame_pair(128, 128, seed=9, n_waves=8)
+    engine.interpolate(x0, x1, DT)
+    aux = {}
+    oracle.interpolate(x0, x1, DT, aux)
+
+    def nhwc(t):
+        return t[0].permute(1, 2, 0).contiguous().numpy().reshape(-1)
+    for l in range(spec.PYRAMID_LEVELS):
+        for k in range(2):
+            got, want = engine.debug_read(f"feat{k}/{l}"), nhwc(aux["feature_pyramids"][k][l])
+            assert np.abs(got - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+        assert np.abs(engine.debug_read(f"res_fwd/{l}") - nhwc(aux["forward_residual_flow_pyramid"][l])).max() < 5e-4
+        assert np.abs(engine.debug_read(f"res_bwd/{l}") - nhwc(aux["backward_residual_flow_pyramid"][l])).max() < 5e-4
+    for l in range(spec.FUSION_PYRAMID_LEVELS):
+        assert np.abs(engine.debug_read(f"flow_fwd/{l}") - nhwc(aux["forward_flow_pyramid"][l])).max() < 5e-3
+        assert np.abs(engine.debug_read(f"flow_bwd/{l}") - nhwc(aux["backward_flow_pyramid"][l])).max() < 5e-3
+        C = spec.feature_channels(l)
+        al = aux["aligned_pyramid"][l]
+        assert np.abs(engine.debug_read(f"warped0/{l}") - nhwc(al[:, 3:3 + C])).max() < 5e-3
+        assert np.abs(engine.debug_read(f"warped1/{l}") - nhwc(al[:, 6 + C:6 + 2 * C])).max() < 5e-3
+
+
+def test_tensor_core_path_agrees_with_cuda_core_validation_path(synthetic_weights):
+    """Same packed weights, same schedule; tcgen05 implicit GEMM vs fp32 FMA kernels."""
+    from frame_interpolation_b200.interpolator import Interpolator
+    x0, x1 = synthetic.frame_pair(128, 192, seed=11, n_waves=8)
+    a = Interpolator(synthetic_weights[0], align=64)
+    b = Interpolator(synthetic_weights[0], align=64)
+    b.set_option("conv_impl", 1)
+    oa, ob = a(x0, x1, DT), b(x0, x1, DT)
+    assert np.abs(oa - ob).max() < 1e-4
+    a.close()
+    b.close()
+
+
+def test_dt_value_is_ignored_and_calls_are_deterministic(engine):
+    x0, x1 = synthetic.frame_pair(128, 128, seed=2, n_waves=8)
+    a = engine(x0, x1, np.full((1,), 0.5, np.float32))
+    b = engine(x0, x1, np.full((1,), 0.1, np.float32))
+    np.testing.assert_array_equal(a, b)
+
+
+def test_batch_of_pairs(engine, oracle):
+    p = [synthetic.frame_pair(64, 128, seed=s, n_waves=6) for s in (0, 1, 2)]
+    x0 = np.concatenate([a for a, _ in p])
+    x1 = np.concatenate([b for _, b in p])
+    out = engine(x0, x1, np.full((3,), 0.5, np.float32))
+    assert out.shape == (3, 64, 128, 3)
+    for i in range(3):
+        np.testing.assert_array_equal(out[i:i + 1], engine(x0[i:i + 1], x1[i:i + 1], DT))
+    assert np.abs(out - oracle(x0, x1, np.full((3,), 0.5, np.float32))).max() < TIGHT
+
+
+def test_tiled_path_matches_oracle_tiled_path_and_per_tile_calls(synthetic_weights):
+    from frame_interpolation_b200.interpolator import Interpolator, image_to_patches
+    from oracle.film_oracle import OracleInterpolator
+    x0, x1 = synthetic.frame_pair(200, 300, seed=12, n_waves=8)      # tiles 100x150 -> each padded to 128x192
+    eng = Interpolator(synthetic_weights[0], align=64, block_shape=[2, 2])
+    out = eng(x0, x1, DT)
+    ref = OracleInterpolator(synthetic_weights[1], align=64, block_shape=[2, 2])(x0, x1, DT)
+    assert out.shape == (1, 200, 300, 3)
+    assert np.abs(out - ref).max() < TIGHT
+    # seams are part of the reference behaviour: every tile equals an independent call on that tile
+    single = Interpolator(synthetic_weights[0], align=64)
+    p0, p1 = image_to_patches(x0, [2, 2]), image_to_patches(x1, [2, 2])
+    for t in range(4):
+        r, c = divmod(t, 2)
+        np.testing.assert_array_equal(out[0, r * 100:(r + 1) * 100, c * 150:(c + 1) * 150],
+                                      single(p0[t][None], p1[t][None], DT)[0])
+    with pytest.raises(AssertionError, match="should evenly divide"):
+        Interpolator(synthetic_weights[0], align=64, block_shape=[3, 2])(x0, x1, DT)
+    eng.close()
+    single.close()
+
+
+def test_argument_errors_mirror_the_reference(engine, synthetic_weights):
+    from frame_interpolation_b200.interpolator import Interpolator
+    x0, x1 = synthetic.frame_pair(64, 64, seed=0, n_waves=4)
+    with pytest.raises(AssertionError):
+        engine(x0[0], x1[0], DT)                                  # rank 3 (eval/interpolator.py:43)
+    with pytest.raises(AssertionError, match="positive"):
+        Interpolator(synthetic_weights[0], align=-8)(x0, x1, DT)  # eval/interpolator.py:44
+    noalign = Interpolator(synthetic_weights[0], align=None)
+    assert noalign(x0, x1, DT).shape == (1, 64, 64, 3)            # already 64-aligned: fine without padding
+    x0b, x1b = synthetic.frame_pair(70, 64, seed=0, n_waves=4)
+    with pytest.raises(AssertionError):
+        noalign(x0b, x1b, DT)                                     # the reference graph fails on unaligned sizes too
+    noalign.close()
+    with pytest.raises(RuntimeError, match="weight"):
+        Interpolator("/nonexistent/weights.filmw")
+
+
+def test_device_pointer_path_bitwise_equals_host_path(engine):
+    import torch
+    x0, x1 = synthetic.frame_pair(120, 200, seed=7, n_waves=8)
+    host = engine(x0, x1, DT)
+    d0, d1 = torch.from_numpy(x0).cuda(), torch.from_numpy(x1).cuda()
+    out = torch.empty_like(d0)
+    torch.cuda.synchronize()
+    engine.interpolate_device(d0.data_ptr(), d1.data_ptr(), 1, 120, 200, out.data_ptr())
+    engine.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), host)
+    # strided views: a tile of a larger device frame in, a tile of a larger frame out
+    big0 = torch.zeros(1, 240, 400, 3, device="cuda")
+    big1 = torch.zeros(1, 240, 400, 3, device="cuda")
+    bigo = torch.zeros(1, 240, 400, 3, device="cuda")
+    big0[0, 120:, 200:] = d0[0]
+    big1[0, 120:, 200:] = d1[0]
+    torch.cuda.synchronize()
+    off = (120 * 400 + 200) * 3 * 4
+    engine.interpolate_device(big0.data_ptr() + off, big1.data_ptr() + off, 1, 120, 200, bigo.data_ptr() + off,
+                              in_pitch=400 * 3, out_pitch=400 * 3)
+    engine.synchronize()
+    np.testing.assert_array_equal(bigo[0, 120:, 200:].cpu().numpy(), host[0])
+    assert float(bigo[0, :120].abs().sum()) == 0.0
+
+
+def test_profile_and_op_table(engine):
+    x0, x1 = synthetic.frame_pair(128, 128, seed=1, n_waves=4)
+    engine(x0, x1, DT)
+    p = engine.profile()
+    assert p["padded_h"] == 128 and p["kernel_launches"] > 100 and p["used_graph"] == 1
+    assert abs(p["conv_flops"] - 2 * spec.conv_macs(128, 128)["total"]) / p["conv_flops"] < 1e-9
+    tab = engine.op_table()
+    assert sum(1 for r in tab if r["category"] == 0) > 60
+    # tensor-core conv FLOPs in the table = all convs but cfeat_conv_0 and the 1x1 heads
+    assert 0.95 < sum(r["ref_flops"] for r in tab if r["category"] == 0) / p["conv_flops"] <= 1.0
+
+
+@pytest.mark.timeout(900)
+def test_full_size_1080p_parity_and_properties(synthetic_weights):
+    """BASELINE.json configs[1] at full size: 1080p against the oracle, plus size-independent
+    properties (tiled 1x1 == untiled, determinism, pad/crop geometry)."""
+    import torch
+    from frame_interpolation_b200.interpolator import Interpolator
+    from oracle.film_oracle import OracleInterpolator
+    x0, x1 = synthetic.frame_pair(1080, 1920, seed=0, n_waves=6)
+    eng = Interpolator(synthetic_weights[0], align=64)
+    out = eng(x0, x1, DT)
+    assert out.shape == (1, 1080, 1920, 3) and np.isfinite(out).all()
+    np.testing.assert_array_equal(out, eng(x0, x1, DT))
+    np.testing.assert_array_equal(out, Interpolator(synthetic_weights[0], align=64, block_shape=[1, 1])(x0, x1, DT))
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    ref = OracleInterpolator(synthetic_weights[1], align=64)(x0, x1, DT)
+    err = np.abs(out.astype(np.float64) - ref).max()
+    assert err < TOL, err
+    assert err < 5e-4, err
+    assert psnr(out, ref) > 80.0
+    eng.close()
