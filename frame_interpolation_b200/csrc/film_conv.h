@@ -52,6 +52,15 @@ struct alignas(64) ConvProblem {
   int out_C, out_c_off;     // channel stride / first channel of the destination slice
   int out_H, out_W;         // destination spatial dims
   int out_sy, out_sx, out_oy, out_ox;  // dest pixel = (y*sy + oy, x*sx + ox)
+  // epilogue mode 1 ("flow head", pyramid_flow_estimator.py:77-83,161): this conv is the 1x1
+  // nf -> nf/2 LeakyReLU layer; the epilogue applies the final linear 1x1 (nf/2 -> 2) on the
+  // fp32 accumulators and adds the upsampled flow:  res = W4^T h + b4 ;  v = res + v_up.
+  int epi_mode;
+  const float* head_w4;   // [cout][2]
+  const float* head_b4;   // [2]
+  const float* head_vup;  // [B][H][W][2] or null (coarsest level)
+  float* head_res;        // [B][H][W][2]
+  float* head_v;          // [B][H][W][2]
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)

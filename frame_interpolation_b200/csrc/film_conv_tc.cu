@@ -38,10 +38,14 @@ template <int BN>
 struct TcCfg {
   static constexpr int kWBytes = BN * kChunk * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
-  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : (BN == 64) ? 4 : 5;
+  // Small-N tiles have short K loops and are bound by per-tile serialisation (prologue ->
+  // mainloop -> epilogue), not by pipeline depth: give them 2 stages and 2 CTAs per SM so one
+  // CTA's epilogue overlaps the other's mainloop (ncu, profiles/r1_ncu_conv.md).
+  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : 2;
+  static constexpr int kMinBlocks = (BN <= 64) ? 2 : 1;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  // stages + barriers (8 B each) + tmem ptr + bias
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + BN * 4;
+  // stages + barriers (8 B each) + tmem ptr + bias + flow-head weights
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + BN * 4 + BN * 8 + 16;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -159,7 +163,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kNumThreads, 1) k_conv_tc(const ConvProblem* __restrict__ prob) {
+__global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const ConvProblem& P = *prob;
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_tc(const ConvProblem* _
   uint32_t* tmem_ptr_smem =
       reinterpret_cast<uint32_t*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
   float* bias_smem = reinterpret_cast<float*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 256);
+  float* w4_smem = bias_smem + BN;  // [BN][2] + b4[2], flow-head mode only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,6 +214,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_tc(const ConvProblem* _
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < BN; i += 128) bias_smem[i] = (n0 + i < P.cout) ? P.bias[n0 + i] : 0.f;
+    if (P.epi_mode == 1) {
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) w4_smem[i] = (i < 2 * P.cout) ? P.head_w4[i] : 0.f;
+      if (threadIdx.x - 64 < 2) w4_smem[2 * BN + threadIdx.x - 64] = P.head_b4[threadIdx.x - 64];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -272,6 +281,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_tc(const ConvProblem* _
     sp_t* ol = P.out_lo + opix * P.out_C + P.out_c_off + n0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (P.epi_mode == 1) {
+      // flow head: hidden = LeakyReLU(acc + b3) stays in fp32 registers; 2-wide linear layer + v_up
+      float r0 = 0.f, r1 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float hdn = leaky(__uint_as_float(v[j]) + bias_smem[cc * 32 + j]);
+          r0 = fmaf(hdn, w4_smem[(cc * 32 + j) * 2], r0);
+          r1 = fmaf(hdn, w4_smem[(cc * 32 + j) * 2 + 1], r1);
+        }
+      }
+      if (valid) {
+        float2 res = make_float2(r0 + w4_smem[2 * BN], r1 + w4_smem[2 * BN + 1]);
+        float2 tot = res;
+        if (P.head_vup) {
+          const float2 u = reinterpret_cast<const float2*>(P.head_vup)[opix];
+          tot.x += u.x;
+          tot.y += u.y;
+        }
+        reinterpret_cast<float2*>(P.head_res)[opix] = res;
+        reinterpret_cast<float2*>(P.head_v)[opix] = tot;
+      }
+    } else
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       if (n0 + cc * 32 >= P.cout) break;

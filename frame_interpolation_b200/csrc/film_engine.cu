@@ -256,6 +256,7 @@ struct Model {
   float *conv0_w = nullptr, *conv0_b = nullptr;  // cfeat_conv_0 [27][64]
   PackedConv fe[8];                              // fe[1..7]
   PackedConv flow[4][3];                         // predictor p, 3x3 conv k
+  PackedConv flow_c3[4];                         // predictor p, 1x1 conv_3 (tensor-core, fused head)
   float *flow_w3[4], *flow_b3[4], *flow_w4[4], *flow_b4[4];
   PackedConv fus_up[4][4];                       // level i, parity class py*2+px
   PackedConv fus_c1[4], fus_c2[4];
@@ -291,6 +292,9 @@ struct Model {
         flow[p][k] = pack_conv(get_tensor(w, pre + std::to_string(k) + "/kernel", {3, 3, nf, nf}),
                                get_tensor(w, pre + std::to_string(k) + "/bias", {nf}),
                                {iota_map(0, nf, round_up(nf, kChunk))}, taps_3x3(), allocs);
+      flow_c3[p] = pack_conv(get_tensor(w, pre + "3/kernel", {1, 1, nf, nf / 2}),
+                             get_tensor(w, pre + "3/bias", {nf / 2}), {iota_map(0, nf, round_up(nf, kChunk))},
+                             {TapSpec{0, 0, {{0, 0}}}}, allocs);
       flow_w3[p] = upload(get_tensor(w, pre + "3/kernel", {1, 1, nf, nf / 2}));
       flow_b3[p] = upload(get_tensor(w, pre + "3/bias", {nf / 2}));
       flow_w4[p] = upload(get_tensor(w, pre + "4/kernel", {1, 1, nf / 2, 2}));
@@ -466,9 +470,9 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 }
 
 // Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
-static void add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
-                     const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
-                     int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
+static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
+                       const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
+                       int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
   const SplitBuf* s0 = sources[0].buf;
@@ -506,17 +510,23 @@ static void add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, co
   const int bn = conv_tc_block_n(pc.cout);
   make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn);
   make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn);
-  cp.out_hi = out->hi;
-  cp.out_lo = out->lo;
-  cp.out_C = out->C;
+  if (out) {
+    cp.out_hi = out->hi;
+    cp.out_lo = out->lo;
+    cp.out_C = out->C;
+    cp.out_H = out->H;
+    cp.out_W = out->W;
+  } else {  // flow-head mode: no split output, pixel index == input grid index
+    cp.out_C = 0;
+    cp.out_H = cp.H;
+    cp.out_W = cp.W;
+  }
   cp.out_c_off = out_c_off;
-  cp.out_H = out->H;
-  cp.out_W = out->W;
   cp.out_sy = sy;
   cp.out_sx = sx;
   cp.out_oy = oy;
   cp.out_ox = ox;
-  if (out->B != cp.B || out_c_off + pc.cout > out->C) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
+  if (out && (out->B != cp.B || out_c_off + pc.cout > out->C)) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   Plan* pp = &P;
@@ -528,6 +538,7 @@ static void add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, co
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
   P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
                  (double)(((pc.cout + bn - 1) / bn) * bn);
+  return idx;
 }
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug) {
@@ -667,7 +678,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0);
     add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0);
     add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0);
-    {
+    if (P.conv_impl == 1) {
+      // CUDA-core validation path keeps the standalone fp32 head kernel
       const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
       float *rr = res[l], *vv = v[l];
       const float* vu = vup;
@@ -675,6 +687,17 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       P.add_op(2, "flow_head" + lt, [=](cudaStream_t st) {
         return launch_flow_head(c2->hi, c2->lo, c2->C, nf, npix, w3, b3, w4, b4, vu, rr, vv, st);
       });
+    } else {
+      // conv_3 (1x1, nf -> nf/2) on the tensor cores; conv_4 + residual add in its epilogue
+      const size_t ci = add_conv(P, "flow_head" + lt, 1.0 * nf * (nf / 2) + (nf / 2) * 2.0, M.flow_c3[p], {{c2, 0}}, 1,
+                                 nullptr, 0);
+      ConvProblem& hp = P.h_probs[ci];
+      hp.epi_mode = 1;
+      hp.head_w4 = M.flow_w4[p];
+      hp.head_b4 = M.flow_b4[p];
+      hp.head_vup = vup;
+      hp.head_res = res[l];
+      hp.head_v = v[l];
     }
     const int64_t np = (int64_t)hh * ww;
     P.debug["flow_fwd/" + std::to_string(l)] = DebugTensor{false, v[l], nullptr, np, 2, 0, 2};
@@ -800,6 +823,7 @@ struct film_handle {
   Plan* last_plan = nullptr;
   std::string err;
   int conv_impl = 0, use_graph = 1, keep_debug = 0, time_ops = 0;
+  bool dev_events_valid = false;  // ev[1]/ev[2] bracket the last device-pointer call
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
 };
@@ -973,6 +997,7 @@ int film_interpolate(film_handle* h, const float* x0, const float* x1, const flo
   try {
     check_frame_args(x0, x1, out, B, H, W);
     FILM_CUDA(cudaSetDevice(h->device));
+    (void)cudaGetLastError();
     Plan* P = get_plan(h, H, W, align);
     const size_t frame = (size_t)H * W * 3 * sizeof(float);
     float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
@@ -1008,6 +1033,7 @@ int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1
     check_frame_args(d_x0, d_x1, d_out, B, H, W);
     if (in_pitch < (int64_t)W * 3 || out_pitch < (int64_t)W * 3) throw Error{FILM_ERR_ARG, "pitch smaller than a row"};
     FILM_CUDA(cudaSetDevice(h->device));
+    (void)cudaGetLastError();
     Plan* P = get_plan(h, H, W, align);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const size_t row = (size_t)W * 3 * sizeof(float);
@@ -1017,13 +1043,14 @@ int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1
                                   cudaMemcpyDeviceToDevice, st));
       FILM_CUDA(cudaMemcpy2DAsync(P->xin + (int64_t)H * W * 3, row, d_x1 + (int64_t)b * H * in_pitch, in_pitch * 4, row, H,
                                   cudaMemcpyDeviceToDevice, st));
-      if (st == h->stream) FILM_CUDA(cudaEventRecord(h->ev[1], st));
+      FILM_CUDA(cudaEventRecord(h->ev[1], st));
       run_plan(h, P, st);
-      if (st == h->stream) FILM_CUDA(cudaEventRecord(h->ev[2], st));
+      FILM_CUDA(cudaEventRecord(h->ev[2], st));
       FILM_CUDA(cudaMemcpy2DAsync(d_out + (int64_t)b * H * out_pitch, out_pitch * 4, P->xout, row, row, H,
                                   cudaMemcpyDeviceToDevice, st));
     }
     fill_profile(h, P, -1.f, 0.f, 0.f);
+    h->dev_events_valid = true;
     return FILM_OK;
   } catch (const Error& e) {
     return fail(h, e);
@@ -1075,11 +1102,13 @@ int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, con
 
 int film_profile(film_handle* h, film_profile_t* out) {
   if (!h || !out) return FILM_ERR_ARG;
-  if (h->prof.last_call_ms < 0 && h->last_plan) {
-    // device-pointer call on the handle's stream: resolve the event pair lazily
+  if (h->prof.last_call_ms < 0 && h->last_plan && h->dev_events_valid) {
+    // device-pointer call: resolve the event pair lazily (blocks until that call finished)
     float t = 0;
     if (cudaEventSynchronize(h->ev[2]) == cudaSuccess && cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess)
       h->prof.last_call_ms = t;
+    else
+      (void)cudaGetLastError();  // never leave a stale error for the next launch check
   }
   *out = h->prof;
   return FILM_OK;
