@@ -157,10 +157,10 @@ def from_named_arrays(arrays: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]
 
 
 def ensure_synthetic_file(path: str | None = None, seed: int = 1234) -> str:
-    """Write the synthetic weight file once (cache dir inside the repo) and return its path."""
+    """Write the synthetic weight file once (cache dir under the system temp dir) and return its path."""
     if path is None:
-        root = os.environ.get("FILM_B200_CACHE",
-                              os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache"))
+        import tempfile
+        root = os.environ.get("FILM_B200_CACHE", os.path.join(tempfile.gettempdir(), "film_b200_cache"))
         os.makedirs(root, exist_ok=True)
         path = os.path.join(root, f"synthetic_seed{seed}.filmw")
     if not os.path.exists(path):
