@@ -414,13 +414,25 @@ struct Plan {
     std::string name;
     double flops;      // reference-graph FLOPs (convs) of this op
     double bytes;      // algorithmic bytes (gathers)
+    int lane;                  // stream lane the op is enqueued on
+    std::vector<int> waits;    // tokens (events) the op waits for before it starts
+    std::vector<int> signals;  // tokens recorded after the op
   };
   std::vector<Op> ops;
   std::vector<float> op_ms;  // filled by timed eager runs
+  // Lanes: independent branches of the graph (the 7 per-scale feature-extractor chains, the
+  // coarse-to-fine flow chain) are enqueued on different streams so that latency-bound coarse
+  // levels overlap with the large fine-level kernels; cross-lane dependencies are tokens (events).
+  static constexpr int kNumLanes = 8;
+  int cur_lane = 0, num_tokens = 0, tok_end = -1;
+  std::vector<int> pending_waits;
+  int new_token() { return num_tokens++; }
   void add_op(int category, const std::string& name, std::function<cudaError_t(cudaStream_t)> fn,
               double flops = 0, double bytes = 0) {
-    ops.push_back(Op{std::move(fn), category, name, flops, bytes});
+    ops.push_back(Op{std::move(fn), category, name, flops, bytes, cur_lane, pending_waits, {}});
+    pending_waits.clear();
   }
+  void signal_last(int token) { ops.back().signals.push_back(token); }
   std::map<std::string, DebugTensor> debug;
   float* xin = nullptr;   // [2][h][w][3] unpadded inputs
   float* xout = nullptr;  // [h][w][3]
@@ -587,13 +599,19 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     P.add_op(2, "image_pool@L" + std::to_string(l), [=](cudaStream_t st) { return launch_image_pool(in, out, 2, hh, ww, st); });
   }
 
+  const int tok_img = P.new_token();
+  P.signal_last(tok_img);
+
   // ---- feature extractor (feature_extractor.py:125-193), Siamese: batch = image index
   SplitBuf* feat[kLevels];
   for (int l = 0; l < kLevels; ++l) feat[l] = P.split(2, Hs[l], Ws[l], feat_channels(l));
   static const int slice_off[4] = {0, 64, 192, 448};
+  int tok_feat[kLevels][kSubLevels];  // token of the conv that completes slice j of feat[i + j]
   for (int i = 0; i < kLevels; ++i) {
     const int depth = (kLevels - i) < kSubLevels ? (kLevels - i) : kSubLevels;
     SplitBuf* pooled = nullptr;
+    P.cur_lane = i;  // one lane per image-pyramid level (independent chains sharing only weights)
+    if (i > 0) P.pending_waits = {tok_img};
     for (int j = 0; j < depth; ++j) {
       const int r = i + j, c = kFilters << j;
       SplitBuf* t1 = P.split(2, Hs[r], Ws[r], c);
@@ -613,6 +631,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       // (replaces the tf.concat at feature_extractor.py:191)
       add_conv(P, "fe_conv" + std::to_string(2 * j + 1) + "@L" + std::to_string(r), 9.0 * c * c, M.fe[2 * j + 1],
                {{t1, 0}}, 1, feat[r], slice_off[j]);
+      tok_feat[i][j] = P.new_token();
+      P.signal_last(tok_feat[i][j]);
       if (j < depth - 1) {
         pooled = P.split(2, Hs[r + 1], Ws[r + 1], c);
         const SplitBuf* f = feat[r];
@@ -639,9 +659,12 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     v[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
     res[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
   }
+  P.cur_lane = Plan::kNumLanes - 1;  // flow + fusion tail lane
   for (int l = kLevels - 1; l >= 0; --l) {
     const int p = l < kSpecialized ? l : kSpecialized;
     const int nf = kFlowFilters[p], C = feat_channels(l), hh = Hs[l], ww = Ws[l];
+    // feat[l] is complete once every sub-pyramid contribution (image level i, depth l - i) is written
+    for (int i = (l - (kSubLevels - 1) > 0 ? l - (kSubLevels - 1) : 0); i <= l; ++i) P.pending_waits.push_back(tok_feat[i][l - i]);
     const SplitBuf* second;  // second operand of concat(a, b)
     float* vup = nullptr;
     if (l == kLevels - 1) {
@@ -771,6 +794,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
                              pp->off_x, pp->h, pp->w, st);
     });
     P.debug["image"] = DebugTensor{false, P.xout, nullptr, (int64_t)h * w, 3, 0, 3};
+    P.tok_end = P.new_token();
+    P.signal_last(P.tok_end);
   }
 
   // reference-graph conv FLOPs (frame_interpolation_b200/spec.py conv_macs)
@@ -824,6 +849,10 @@ struct film_handle {
   std::string err;
   int conv_impl = 0, use_graph = 1, keep_debug = 0, time_ops = 0;
   bool dev_events_valid = false;  // ev[1]/ev[2] bracket the last device-pointer call
+  cudaStream_t lane_streams[Plan::kNumLanes] = {};  // lane 0 = the origin stream of the call
+  std::vector<cudaEvent_t> token_events;
+  cudaEvent_t fork_event = nullptr;
+  int use_lanes = 1;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
 };
@@ -835,6 +864,38 @@ static int fail(film_handle* h, const Error& e) {
   return e.code;
 }
 
+// Enqueues the whole schedule with `origin` as lane 0: fork the other lanes from it, express
+// cross-lane dependencies with events, join everything back into `origin`.  Works both eagerly and
+// under stream capture (the events become graph edges).
+static void enqueue_plan(film_handle* h, Plan* P, cudaStream_t origin) {
+  if (!h->use_lanes) {
+    for (auto& op : P->ops) FILM_CUDA(op.fn(origin));
+    return;
+  }
+  if (!h->fork_event) FILM_CUDA(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+  for (int i = 1; i < Plan::kNumLanes; ++i)
+    if (!h->lane_streams[i]) FILM_CUDA(cudaStreamCreateWithFlags(&h->lane_streams[i], cudaStreamNonBlocking));
+  while ((int)h->token_events.size() < P->num_tokens) {
+    cudaEvent_t e;
+    FILM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->token_events.push_back(e);
+  }
+  auto lane_stream = [&](int lane) { return lane == 0 ? origin : h->lane_streams[lane]; };
+  FILM_CUDA(cudaEventRecord(h->fork_event, origin));
+  bool forked[Plan::kNumLanes] = {true};
+  for (auto& op : P->ops) {
+    cudaStream_t st = lane_stream(op.lane);
+    if (!forked[op.lane]) {
+      FILM_CUDA(cudaStreamWaitEvent(st, h->fork_event, 0));
+      forked[op.lane] = true;
+    }
+    for (int t : op.waits) FILM_CUDA(cudaStreamWaitEvent(st, h->token_events[t], 0));
+    FILM_CUDA(op.fn(st));
+    for (int t : op.signals) FILM_CUDA(cudaEventRecord(h->token_events[t], st));
+  }
+  if (P->tok_end >= 0) FILM_CUDA(cudaStreamWaitEvent(origin, h->token_events[P->tok_end], 0));
+}
+
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d", hh, ww, align > 0 ? align : 0, h->conv_impl);
@@ -844,14 +905,15 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = cudaSuccess;
-    for (auto& op : p->ops) {
-      e = op.fn(h->stream);
-      if (e != cudaSuccess) break;
+    try {
+      enqueue_plan(h, p.get(), h->stream);
+    } catch (const Error& err) {
+      cudaStreamEndCapture(h->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+      throw Error{FILM_ERR_CUDA, "kernel launch failed during capture: " + err.msg};
     }
-    cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
-    if (e != cudaSuccess) throw Error{FILM_ERR_CUDA, std::string("kernel launch failed during capture: ") + cudaGetErrorString(e)};
-    FILM_CUDA(e2);
+    FILM_CUDA(cudaStreamEndCapture(h->stream, &g));
     FILM_CUDA(cudaGraphInstantiate(&p->graph, g, 0));
     cudaGraphDestroy(g);
   }
@@ -882,7 +944,7 @@ static void run_plan(film_handle* h, Plan* P, cudaStream_t st) {
       P->op_ms.assign(n, 0.f);
       for (size_t i = 0; i < n; ++i) FILM_CUDA(cudaEventElapsedTime(&P->op_ms[i], h->op_events[i], h->op_events[i + 1]));
     } else {
-      for (auto& op : P->ops) FILM_CUDA(op.fn(st));
+      enqueue_plan(h, P, st);
     }
   }
   h->last_plan = P;
@@ -939,6 +1001,10 @@ void film_destroy(film_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->op_events) cudaEventDestroy(e);
+  for (auto& e : h->token_events) cudaEventDestroy(e);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
+  for (int i = 1; i < Plan::kNumLanes; ++i)
+    if (h->lane_streams[i]) cudaStreamDestroy(h->lane_streams[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -952,6 +1018,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "use_graph") h->use_graph = value;
   else if (n == "keep_debug") h->keep_debug = value;
   else if (n == "time_ops") h->time_ops = value;
+  else if (n == "use_lanes") h->use_lanes = value;
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;

@@ -172,7 +172,7 @@ class Oracle:
                  conv_hook: Optional[Callable] = None, num_threads: Optional[int] = None):
         self.dtype = dtype
         self.w = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in weights.items()}
-        # conv_hook(x, kernel) -> (x', kernel') lets error-budget studies emulate reduced
+        # conv_hook(x, kernel, layer_name) -> (x', kernel') lets error-budget studies emulate reduced
         # precision operand formats; None for the oracle proper.
         self.conv_hook = conv_hook
         if num_threads:
@@ -181,7 +181,7 @@ class Oracle:
     def _conv(self, x: Tensor, name: str, activation: bool) -> Tensor:
         k, b = self.w[name + "/kernel"], self.w[name + "/bias"]
         if self.conv_hook is not None:
-            x, k = self.conv_hook(x, k)
+            x, k = self.conv_hook(x, k, name)
         return conv2d_same(x, k, b, activation)
 
     # feature_extractor.py:125-147
