@@ -61,11 +61,20 @@ struct alignas(64) ConvProblem {
   const float* head_vup;  // [B][H][W][2] or null (coarsest level)
   float* head_res;        // [B][H][W][2]
   float* head_v;          // [B][H][W][2]
+  // persistent 3x3 kernel (film_conv3x3_tc.cu): tile is fixed 16 x 8, taps are dx-major,
+  // tm_a_* boxes are (64 ch, 8 px, 18 rows).  Pipeline shape chosen on the host:
+  int v2_resident;        // 1: all W_hi/W_lo K blocks stay in shared memory for the CTA's lifetime
+  int v2_na, v2_nw;       // activation-ring / weight-ring stages
+  int v2_grid;            // persistent CTAs
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)
 cudaError_t launch_conv_tc(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
 cudaError_t launch_conv_simt(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
 cudaError_t conv_tc_configure();  // cudaFuncSetAttribute for all instantiations
+// persistent 3x3 variant: fills the v2_* fields of `h_prob` (call before uploading the problem)
+void conv3x3_tc_plan(ConvProblem& h_prob, int num_sms);
+cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
+cudaError_t conv3x3_tc_configure();
 
 }  // namespace film

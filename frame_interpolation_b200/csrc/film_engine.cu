@@ -209,10 +209,12 @@ static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
   return pc;
 }
 
+// dx-major tap order (kx outer, ky inner): the persistent 3x3 kernel consumes the three dy taps of
+// one dx-shifted activation box back to back (film_conv3x3_tc.cu); the generic kernel is order-agnostic.
 static std::vector<TapSpec> taps_3x3() {
   std::vector<TapSpec> t;
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) t.push_back({ky - 1, kx - 1, {{ky, kx}}});
+  for (int kx = 0; kx < 3; ++kx)
+    for (int ky = 0; ky < 3; ++ky) t.push_back({ky - 1, kx - 1, {{ky, kx}}});
   return t;
 }
 // fusion.py:133-135: NN 2x upsample followed by a 2x2 SAME conv (pad bottom/right), evaluated on
@@ -404,6 +406,7 @@ struct DebugTensor {
 struct Plan {
   int h, w, H, W, off_y, off_x;
   int conv_impl;
+  int conv3x3_v2 = 1, num_sms = 148;
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -493,7 +496,19 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.B = s0->B;
   cp.H = s0->H;
   cp.W = s0->W;
-  pick_tile(cp.H, cp.W, cp.tile_h, cp.tile_w);
+  // 3x3 SAME convs with a unit-stride destination run on the persistent tap-reuse kernel
+  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1;
+  int box_h, box_w;
+  if (v2) {
+    cp.tile_h = 16;
+    cp.tile_w = 8;
+    box_h = 18;
+    box_w = 8;
+  } else {
+    pick_tile(cp.H, cp.W, cp.tile_h, cp.tile_w);
+    box_h = cp.tile_h;
+    box_w = cp.tile_w;
+  }
   cp.tiles_y = (cp.H + cp.tile_h - 1) / cp.tile_h;
   cp.tiles_x = (cp.W + cp.tile_w - 1) / cp.tile_w;
   for (int s = 0; s < cp.nsrc; ++s) {
@@ -505,8 +520,8 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     cp.src[s].c_off = sources[s].c_off;
     cp.src[s].nchunk = pc.src_chunks[s];
     if (sources[s].c_off + pc.src_chunks[s] * kChunk > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
-    make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, cp.tile_h, cp.tile_w);
-    make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, cp.tile_h, cp.tile_w);
+    make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w);
+    make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w);
   }
   cp.ntaps = pc.ntaps;
   for (int t = 0; t < pc.ntaps; ++t) {
@@ -539,13 +554,15 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.out_oy = oy;
   cp.out_ox = ox;
   if (out && (out->B != cp.B || out_c_off + pc.cout > out->C)) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
+  if (v2) conv3x3_tc_plan(cp, P.num_sms);
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   Plan* pp = &P;
   const int impl = P.conv_impl;
-  P.add_op(0, tag, [pp, idx, impl](cudaStream_t st) {
-    return impl == 1 ? launch_conv_simt(pp->d_probs + idx, pp->h_probs[idx], st)
-                     : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
+  P.add_op(0, tag, [pp, idx, impl, v2](cudaStream_t st) {
+    if (impl == 1) return launch_conv_simt(pp->d_probs + idx, pp->h_probs[idx], st);
+    return v2 ? launch_conv3x3_tc(pp->d_probs + idx, pp->h_probs[idx], st)
+              : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
   }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W);
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
   P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
@@ -553,12 +570,15 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   return idx;
 }
 
-static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug) {
+static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
+                                        int conv3x3_v2, int num_sms) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
   P.h = h;
   P.w = w;
   P.conv_impl = conv_impl;
+  P.conv3x3_v2 = conv3x3_v2;
+  P.num_sms = num_sms;
   // eval/interpolator.py:30-63
   int ph = 0, pw = 0;
   if (align > 0) {
@@ -852,7 +872,9 @@ struct film_handle {
   cudaStream_t lane_streams[Plan::kNumLanes] = {};  // lane 0 = the origin stream of the call
   std::vector<cudaEvent_t> token_events;
   cudaEvent_t fork_event = nullptr;
-  int use_lanes = 1;
+  int use_lanes = 0;   // stream lanes measured no gain at 1080p (smem-saturating kernels cannot co-reside)
+  int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
+  int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
 };
@@ -898,10 +920,12 @@ static void enqueue_plan(film_handle* h, Plan* P, cudaStream_t origin) {
 
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
-  snprintf(key, sizeof(key), "%dx%d_a%d_i%d", hh, ww, align > 0 ? align : 0, h->conv_impl);
+  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
+           h->use_lanes);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
-  std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0);
+  std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2,
+                                       h->num_sms);
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -980,6 +1004,8 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     FILM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) FILM_CUDA(cudaEventCreate(&e));
     FILM_CUDA(conv_tc_configure());
+    FILM_CUDA(conv3x3_tc_configure());
+    h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
     h->model.reset(new Model);
     h->model->load(w);
@@ -1019,6 +1045,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "keep_debug") h->keep_debug = value;
   else if (n == "time_ops") h->time_ops = value;
   else if (n == "use_lanes") h->use_lanes = value;
+  else if (n == "conv3x3_v2") h->conv3x3_v2 = value;
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;

@@ -110,7 +110,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                       tests to cross-check the tensor-core path on the device)
  *   "use_graph"   : 1 = capture each shape's schedule in a CUDA graph (default), 0 = eager
  *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read
- *   "time_ops"    : 1 = run eagerly with one CUDA-event pair per kernel (see film_op_table) */
+ *   "time_ops"    : 1 = run eagerly with one CUDA-event pair per kernel (see film_op_table)
+ *   "conv3x3_v2"  : 1 = persistent tap-reuse kernel for 3x3 convs (default), 0 = generic kernel
+ *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0) */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
 
 /* Debug/parity hook: copies an intermediate tensor of the LAST call to host as float32
