@@ -44,7 +44,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
   const int NA = P.v2_na, NW = P.v2_nw;
   const bool resident = P.v2_resident != 0;
   constexpr int kWTap = BN * 128 * 2;
-  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  // Fused-N product (BN <= 128): SS-mode MMAs with small N are bound by the shared-memory read of
+  // the A operand (~64 B/clk -> ~64-85 cycles per M=128,K=16 instruction, measured), not by math.
+  // W_hi and W_lo blocks are contiguous in smem, so  A_hi x [W_hi ; W_lo]  is ONE MMA with N = 2*BN
+  // (columns [0,BN) = hi*hi, [BN,2BN) = hi*lo) and  A_lo x W_hi  accumulates into columns [0,BN):
+  // 2 A-operand reads per k-step instead of 3.  The epilogue adds the two column halves.
+  constexpr bool kFused = BN <= 128;
+  constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   int nkb = 0;  // K blocks = (source, chunk, dx, dy)
   for (int s = 0; s < P.nsrc; ++s) nkb += P.src[s].nchunk * 9;
@@ -115,10 +122,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             for (int dx = 0; dx < 3; ++dx) {
               const int st = ia % NA;
               mbar_wait(a_empty(st), ((ia / NA) & 1u) ^ 1u);
-              mbar_expect_tx(a_full(st), kAStage);
               const uint32_t sa = a_base + st * kAStage;
-              tma_load_4d(sa, &P.tm_a_hi[s], a_full(st), c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
-              tma_load_4d(sa + kAPlane, &P.tm_a_lo[s], a_full(st), c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
+              if ((P.dbg_flags & 2) && ia >= (uint32_t)NA) {
+                mbar_arrive(a_full(st));
+              } else {
+                mbar_expect_tx(a_full(st), kAStage);
+                tma_load_4d(sa, &P.tm_a_hi[s], a_full(st), c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
+                tma_load_4d(sa + kAPlane, &P.tm_a_lo[s], a_full(st), c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
+              }
               ++ia;
               if (!resident) {
                 for (int dy = 0; dy < 3; ++dy, ++kb) {
@@ -140,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc<BN>();
+      const uint32_t idesc2 = make_idesc<(kFused ? 2 * BN : BN)>();
       if (resident) {
         mbar_wait(w_full(0), 0);
         tc_fence_after();
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         const uint32_t acc = it & 1u;
         mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
         int kb = 0;
         bool first = true;
         const int nab = nkb / 3;  // activation stages per tile
@@ -171,13 +183,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             }
             const uint64_t a_hi = make_desc(sa + dy * 1024), a_lo = make_desc(sa + kAPlane + dy * 1024);
             const uint64_t w_hi = make_desc(sw), w_lo = make_desc(sw + kWTap / 2);
+            if (!(P.dbg_flags & 4)) {
 #pragma unroll
-            for (int k = 0; k < kChunk / 16; ++k) {
-              const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              umma(d_tmem, a_lo + adv, w_hi + adv, idesc, first ? 0u : 1u);
-              first = false;
-              umma(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-              umma(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              for (int k = 0; k < kChunk / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                if constexpr (kFused) {
+                  umma(d_tmem, a_hi + adv, w_hi + adv, idesc2, first ? 0u : 1u);  // N = 2*BN: [W_hi ; W_lo]
+                  first = false;
+                  umma(d_tmem, a_lo + adv, w_hi + adv, idesc, 1u);
+                } else {
+                  umma(d_tmem, a_lo + adv, w_hi + adv, idesc, first ? 0u : 1u);
+                  first = false;
+                  umma(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                  umma(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+                }
+              }
             }
             if (!resident) {
               umma_commit(w_empty(ws));
@@ -206,14 +226,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       sp_t* ol = P.out_lo + opix * P.out_C + P.out_c_off + n0;
       mbar_wait(t_full(acc), (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         if (n0 + cc * 32 >= P.cout) break;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
-        tmem_ld_wait();
-        if (valid) {
+        if constexpr (kFused) {
+          uint32_t u[32];
+          tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        } else {
+          tmem_ld_wait();
+        }
+        if (valid && !(P.dbg_flags & 1)) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];

@@ -45,7 +45,9 @@ struct TcCfg {
   // CTA's epilogue overlaps the other's mainloop (ncu, profiles/r1_ncu_conv.md).
   static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : 2;
   static constexpr int kMinBlocks = (BN <= 64) ? 2 : 1;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // fused-N product for BN <= 128 (see film_conv3x3_tc.cu): accumulator = 2*BN columns
+  static constexpr bool kFused = BN <= 128;
+  static constexpr int kTmemCols = kFused ? 2 * BN : BN;
   // stages + barriers (8 B each) + tmem ptr + bias + flow-head weights
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + BN * 4 + BN * 8 + 16;
 };
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc<BN>();
+      const uint32_t idesc2 = make_idesc<(Cfg::kFused ? 2 * BN : BN)>();
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % Cfg::kStages;
         const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
@@ -149,9 +152,14 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
 #pragma unroll
         for (int k = 0; k < kChunk / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 elements x 2 B = 32 B along K
-          umma(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma(tmem_base, a_hi + adv, w_lo + adv, idesc, 1u);
-          umma(tmem_base, a_hi + adv, w_hi + adv, idesc, 1u);
+          if constexpr (Cfg::kFused) {
+            umma(tmem_base, a_hi + adv, w_hi + adv, idesc2, (kb | k) != 0 ? 1u : 0u);  // [W_hi ; W_lo]
+            umma(tmem_base, a_lo + adv, w_hi + adv, idesc, 1u);
+          } else {
+            umma(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma(tmem_base, a_hi + adv, w_lo + adv, idesc, 1u);
+            umma(tmem_base, a_hi + adv, w_hi + adv, idesc, 1u);
+          }
         }
         umma_commit(empty_bar(stage));
       }
@@ -176,7 +184,15 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-        tmem_ld_wait();
+        if constexpr (Cfg::kFused) {
+          uint32_t u[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cc * 32), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        } else {
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float hdn = leaky(__uint_as_float(v[j]) + bias_smem[cc * 32 + j]);
@@ -201,7 +217,15 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
       if (n0 + cc * 32 >= P.cout) break;
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-      tmem_ld_wait();
+      if constexpr (Cfg::kFused) {
+        uint32_t u[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cc * 32), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      } else {
+        tmem_ld_wait();
+      }
       if (valid) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {

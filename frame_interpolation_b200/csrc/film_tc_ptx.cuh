@@ -80,7 +80,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format=F32 [4,6),
 // a_format [7,10), b_format [10,13) (0 = F16, 1 = BF16), K-major A and B, N>>3 [17,23), M>>4 [24,29).
 template <int BN>
-__device__ __forceinline__ uint32_t make_idesc() {
+__device__ __forceinline__ uint32_t make_idesc() {  // BN = MMA N extent
 #ifdef FILM_SPLIT_FP16
   constexpr uint32_t fmt = 0;
 #else
