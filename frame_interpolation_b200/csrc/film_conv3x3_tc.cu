@@ -15,7 +15,9 @@
 //  * Persistent CTAs (grid = #SMs) walk a static tile list; the fp32 accumulator is double-buffered
 //    in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Roles: warp 0 = TMA producer (+ L2 prefetch of the next tile's boxes: the first touch of an
+// activation tile comes from DRAM, ~2.5 us under load, and the ring holds only 2-4 stages),
+// warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +29,8 @@ namespace film {
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kBoxRows = (kTileH + 2) * kTileW;     // 144 pixel rows per dx-copy
 constexpr int kAPlane = kBoxRows * 128;             // 18432 B
@@ -87,13 +90,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), 4);  // one arrive per epilogue warp
+      mbar_init(t_empty(s), kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
   if (warp >= 2)
-    for (int i = threadIdx.x - 64; i < n_nt * BN; i += 128) bias_smem[i] = (i < P.cout) ? P.bias[i] : 0.f;
+    for (int i = threadIdx.x - 64; i < n_nt * BN; i += 32 * kEpiWarps) bias_smem[i] = (i < P.cout) ? P.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,6 +118,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         const int sp = tile / n_nt, n0 = (tile % n_nt) * BN;
         const int b = sp / tiles_per_img, rem = sp % tiles_per_img;
         const int y0 = (rem / P.tiles_x) * kTileH, x0 = (rem % P.tiles_x) * kTileW;
+        {
+          // L2 prefetch of this CTA's NEXT spatial tile (skip if it is the same spatial tile, other N half)
+          const int nt = tile + gridDim.x;
+          if (nt < ntiles && nt / n_nt != sp) {
+            const int nsp = nt / n_nt, nb = nsp / tiles_per_img, nrem = nsp % tiles_per_img;
+            const int ny0 = (nrem / P.tiles_x) * kTileH, nx0 = (nrem % P.tiles_x) * kTileW;
+            for (int s = 0; s < P.nsrc; ++s)
+              for (int ch = 0; ch < P.src[s].nchunk; ++ch) {
+                // the three dx boxes overlap: one 10-px-wide region == boxes at dx = 0 and dx = 2
+                tma_prefetch_4d(&P.tm_a_hi[s], P.src[s].c_off + ch * kChunk, nx0 - 1, ny0 - 1, nb);
+                tma_prefetch_4d(&P.tm_a_hi[s], P.src[s].c_off + ch * kChunk, nx0 + 1, ny0 - 1, nb);
+                tma_prefetch_4d(&P.tm_a_lo[s], P.src[s].c_off + ch * kChunk, nx0 - 1, ny0 - 1, nb);
+                tma_prefetch_4d(&P.tm_a_lo[s], P.src[s].c_off + ch * kChunk, nx0 + 1, ny0 - 1, nb);
+              }
+          }
+        }
         int kb = 0;
         for (int s = 0; s < P.nsrc; ++s) {
           const int nchunk = P.src[s].nchunk, c_off = P.src[s].c_off;
@@ -211,8 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       }
     }
   } else {
-    // ============================ epilogue (warps 2..5) ============================
-    const int q = warp & 3;
+    // ============================ epilogue (warps 2..9) ============================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which 16-column chunks (even / odd) this warp drains
     const int r = q * 32 + lane;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -228,32 +248,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        if (n0 + cc * 32 >= P.cout) break;
-        uint32_t v[32];
-        tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
+      for (int cc = half; cc < BN / 16; cc += 2) {
+        if (n0 + cc * 16 >= P.cout) break;
+        uint32_t v[16];
+        tmem_ld16(t_addr + (uint32_t)(cc * 16), v);
         if constexpr (kFused) {
-          uint32_t u[32];
-          tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
+          uint32_t u[16];
+          tmem_ld16(t_addr + (uint32_t)(BN + cc * 16), u);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
         } else {
           tmem_ld_wait();
         }
         if (valid && !(P.dbg_flags & 1)) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 32 + g * 8 + j];
+              float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 16 + g * 8 + j];
               f[j] = P.act ? leaky(x) : x;
             }
             uint4 h, l;
             pack8(f, h, l);
-            *reinterpret_cast<uint4*>(oh + cc * 32 + g * 8) = h;
-            *reinterpret_cast<uint4*>(ol + cc * 32 + g * 8) = l;
+            *reinterpret_cast<uint4*>(oh + cc * 16 + g * 8) = h;
+            *reinterpret_cast<uint4*>(ol + cc * 16 + g * 8) = l;
           }
         }
       }
