@@ -66,8 +66,6 @@ struct alignas(64) ConvProblem {
   int v2_resident;        // 1: all W_hi/W_lo K blocks stay in shared memory for the CTA's lifetime
   int v2_na, v2_nw;       // activation-ring / weight-ring stages
   int v2_grid;            // persistent CTAs
-  int dbg_flags;          // bottleneck experiments only (env FILM_DBG_FLAGS): 1 = no epilogue stores,
-                          // 2 = no activation TMA loads after the first ring fill, 4 = no MMA issue
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)

@@ -56,7 +56,6 @@ template <int BN>
 __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  const ConvProblem& P = *prob;
 
   // carve shared memory (1024 B alignment required by SWIZZLE_128B)
   const uint32_t raw = smem_u32(smem_raw);
@@ -75,17 +74,21 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // problem fields -> registers once (asm "memory" clobbers would otherwise reload them from global)
+  const int nsrc = prob->nsrc, ntaps = prob->ntaps, cout = prob->cout, epi_mode = prob->epi_mode;
+  const int tile_h = prob->tile_h, tile_w = prob->tile_w, tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
+
   // tile coordinates
   int tile = blockIdx.x;
-  const int tx = tile % P.tiles_x;
-  tile /= P.tiles_x;
-  const int ty = tile % P.tiles_y;
-  const int b = tile / P.tiles_y;
-  const int y0 = ty * P.tile_h, x0 = tx * P.tile_w;
+  const int tx = tile % tiles_x;
+  tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int b = tile / tiles_y;
+  const int y0 = ty * tile_h, x0 = tx * tile_w;
   const int n0 = blockIdx.y * BN;
 
   int nkb = 0;
-  for (int s = 0; s < P.nsrc; ++s) nkb += P.src[s].nchunk * P.ntaps;
+  for (int s = 0; s < nsrc; ++s) nkb += prob->src[s].nchunk * ntaps;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -95,18 +98,12 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), (uint32_t)Cfg::kTmemCols);
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_smem[i] = (n0 + i < P.cout) ? P.bias[n0 + i] : 0.f;
-    if (P.epi_mode == 1) {
-      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) w4_smem[i] = (i < 2 * P.cout) ? P.head_w4[i] : 0.f;
-      if (threadIdx.x - 64 < 2) w4_smem[2 * BN + threadIdx.x - 64] = P.head_b4[threadIdx.x - 64];
+    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_smem[i] = (n0 + i < cout) ? prob->bias[n0 + i] : 0.f;
+    if (epi_mode == 1) {
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) w4_smem[i] = (i < 2 * cout) ? prob->head_w4[i] : 0.f;
+      if (threadIdx.x - 64 < 2) w4_smem[2 * BN + threadIdx.x - 64] = prob->head_b4[threadIdx.x - 64];
     }
   }
   tc_fence_before();
@@ -115,78 +112,91 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int kb = 0;
-      for (int s = 0; s < P.nsrc; ++s) {
-        const int nchunk = P.src[s].nchunk, c_off = P.src[s].c_off;
-        for (int ch = 0; ch < nchunk; ++ch) {
-          for (int t = 0; t < P.ntaps; ++t, ++kb) {
-            const int stage = kb % Cfg::kStages;
-            const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+    // ===================== TMA producer (warp-uniform, elected lane issues) =====================
+    const CUtensorMap* tm_w_hi = &prob->tm_w_hi;
+    const CUtensorMap* tm_w_lo = &prob->tm_w_lo;
+    int kb = 0;
+    for (int s = 0; s < nsrc; ++s) {
+      const int nchunk = prob->src[s].nchunk, c_off = prob->src[s].c_off;
+      const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
+      const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
+      for (int ch = 0; ch < nchunk; ++ch) {
+        for (int t = 0; t < ntaps; ++t, ++kb) {
+          const int stage = kb % Cfg::kStages;
+          const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
+          const int xx = x0 + prob->tap_dx[t], yy = y0 + prob->tap_dy[t];
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (elect_one()) {
             const uint32_t sa = base + stage * Cfg::kStageBytes;
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            const int cc = c_off + ch * kChunk, xx = x0 + P.tap_dx[t], yy = y0 + P.tap_dy[t];
-            tma_load_4d(sa, &P.tm_a_hi[s], full_bar(stage), cc, xx, yy, b);
-            tma_load_4d(sa + kABytes, &P.tm_a_lo[s], full_bar(stage), cc, xx, yy, b);
-            tma_load_2d(sa + 2 * kABytes, &P.tm_w_hi, full_bar(stage), kb * kChunk, n0);
-            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, &P.tm_w_lo, full_bar(stage), kb * kChunk, n0);
+            const int cc = c_off + ch * kChunk;
+            tma_load_4d(sa, tm_hi, full_bar(stage), cc, xx, yy, b);
+            tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, b);
+            tma_load_2d(sa + 2 * kABytes, tm_w_hi, full_bar(stage), kb * kChunk, n0);
+            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * kChunk, n0);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc<BN>();
-      const uint32_t idesc2 = make_idesc<(Cfg::kFused ? 2 * BN : BN)>();
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int stage = kb % Cfg::kStages;
-        const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
+    // ===================== MMA issuer (warp-uniform, elected lane issues) =====================
+    const uint32_t idesc = make_idesc<BN>();
+    const uint32_t idesc2 = make_idesc<(Cfg::kFused ? 2 * BN : BN)>();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int stage = kb % Cfg::kStages;
+      const uint32_t phase = (uint32_t)(kb / Cfg::kStages) & 1u;
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = base + stage * Cfg::kStageBytes;
         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kABytes);
         const uint64_t w_hi = make_desc(sa + 2 * kABytes), w_lo = make_desc(sa + 2 * kABytes + Cfg::kWBytes);
+        const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
         for (int k = 0; k < kChunk / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 elements x 2 B = 32 B along K
           if constexpr (Cfg::kFused) {
-            umma(tmem_base, a_hi + adv, w_hi + adv, idesc2, (kb | k) != 0 ? 1u : 0u);  // [W_hi ; W_lo]
+            umma(tmem_base, a_hi + adv, w_hi + adv, idesc2, k == 0 ? first : 1u);  // [W_hi ; W_lo]
             umma(tmem_base, a_lo + adv, w_hi + adv, idesc, 1u);
           } else {
-            umma(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma(tmem_base, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
             umma(tmem_base, a_hi + adv, w_lo + adv, idesc, 1u);
             umma(tmem_base, a_hi + adv, w_hi + adv, idesc, 1u);
           }
         }
         umma_commit(empty_bar(stage));
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // tile row == TMEM lane
-    const int py = y0 + r / P.tile_w, px = x0 + r % P.tile_w;
-    const bool valid = (py < P.H) && (px < P.W);
-    const int64_t opix =
-        ((int64_t)b * P.out_H + ((int64_t)py * P.out_sy + P.out_oy)) * P.out_W + ((int64_t)px * P.out_sx + P.out_ox);
-    sp_t* oh = P.out_hi + opix * P.out_C + P.out_c_off + n0;
-    sp_t* ol = P.out_lo + opix * P.out_C + P.out_c_off + n0;
+    const int py = y0 + r / tile_w, px = x0 + r % tile_w;
+    const bool valid = (py < prob->H) && (px < prob->W);
+    const int64_t opix = ((int64_t)b * prob->out_H + ((int64_t)py * prob->out_sy + prob->out_oy)) * prob->out_W +
+                         ((int64_t)px * prob->out_sx + prob->out_ox);
+    const int act = prob->act;
+    sp_t* oh = prob->out_hi + opix * prob->out_C + prob->out_c_off + n0;
+    sp_t* ol = prob->out_lo + opix * prob->out_C + prob->out_c_off + n0;
+    const float* head_vup = prob->head_vup;
+    float* head_res = prob->head_res;
+    float* head_v = prob->head_v;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    if (P.epi_mode == 1) {
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (epi_mode == 1) {
       // flow head: hidden = LeakyReLU(acc + b3) stays in fp32 registers; 2-wide linear layer + v_up
       float r0 = 0.f, r1 = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+        tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
         if constexpr (Cfg::kFused) {
           uint32_t u[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cc * 32), u);
+          tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
@@ -203,42 +213,43 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
       if (valid) {
         float2 res = make_float2(r0 + w4_smem[2 * BN], r1 + w4_smem[2 * BN + 1]);
         float2 tot = res;
-        if (P.head_vup) {
-          const float2 u = reinterpret_cast<const float2*>(P.head_vup)[opix];
+        if (head_vup) {
+          const float2 u = reinterpret_cast<const float2*>(head_vup)[opix];
           tot.x += u.x;
           tot.y += u.y;
         }
-        reinterpret_cast<float2*>(P.head_res)[opix] = res;
-        reinterpret_cast<float2*>(P.head_v)[opix] = tot;
+        reinterpret_cast<float2*>(head_res)[opix] = res;
+        reinterpret_cast<float2*>(head_v)[opix] = tot;
       }
-    } else
+    } else {
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      if (n0 + cc * 32 >= P.cout) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-      if constexpr (Cfg::kFused) {
-        uint32_t u[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cc * 32), u);
-        tmem_ld_wait();
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        if (n0 + cc * 32 >= cout) break;
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
+        if constexpr (Cfg::kFused) {
+          uint32_t u[32];
+          tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-      } else {
-        tmem_ld_wait();
-      }
-      if (valid) {
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        } else {
+          tmem_ld_wait();
+        }
+        if (valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = __uint_as_float(v[g * 8 + j]) + bias_smem[cc * 32 + g * 8 + j];
-            f[j] = P.act ? leaky(x) : x;
+            for (int j = 0; j < 8; ++j) {
+              float x = __uint_as_float(v[g * 8 + j]) + bias_smem[cc * 32 + g * 8 + j];
+              f[j] = act ? leaky(x) : x;
+            }
+            uint4 h, l;
+            pack8(f, h, l);
+            *reinterpret_cast<uint4*>(oh + cc * 32 + g * 8) = h;
+            *reinterpret_cast<uint4*>(ol + cc * 32 + g * 8) = l;
           }
-          uint4 h, l;
-          pack8(f, h, l);
-          *reinterpret_cast<uint4*>(oh + cc * 32 + g * 8) = h;
-          *reinterpret_cast<uint4*>(ol + cc * 32 + g * 8) = l;
         }
       }
     }
@@ -247,9 +258,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)Cfg::kTmemCols)
-                 : "memory");
+    tmem_dealloc(tmem_base, (uint32_t)Cfg::kTmemCols);
   }
 }
 

@@ -555,8 +555,6 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.out_ox = ox;
   if (out && (out->B != cp.B || out_c_off + pc.cout > out->C)) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
   if (v2) conv3x3_tc_plan(cp, P.num_sms);
-  if (const char* dbg = getenv("FILM_DBG_FLAGS")) cp.dbg_flags = atoi(dbg);
-  if (const char* na = getenv("FILM_DBG_NA")) { if (v2 && atoi(na) > 0 && atoi(na) < cp.v2_na) cp.v2_na = atoi(na); }
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   Plan* pp = &P;

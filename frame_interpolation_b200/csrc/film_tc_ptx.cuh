@@ -142,6 +142,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// Warp-uniform leader election.  Role loops are executed by all 32 lanes (converged) and only the
+// elected lane issues TMA / tcgen05 instructions: with `if (lane == 0)` around a whole role the
+// compiler wraps every uniform-datapath instruction (UTCHMMA, UTMALDG) in ELECT/BRA.U.ANY
+// divergence loops and the single issuing thread becomes the bottleneck (ncu, profiles/).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
