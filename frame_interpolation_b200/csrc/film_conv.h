@@ -17,7 +17,8 @@ namespace film {
 
 constexpr int kMaxSrc = 4;
 constexpr int kMaxTaps = 9;
-constexpr int kChunk = 64;   // channels per K block (64 x 2 B = one 128 B swizzle row)
+constexpr int kChunk = 64;   // default channels per K block (64 x 2 B = one 128 B swizzle row)
+                             // ConvProblem::kchunk may be 32 (64 B rows, SWIZZLE_64B) for 32-channel layers
 constexpr int kTileM = 128;  // output pixels per CTA tile (tile_h x tile_w)
 
 struct ConvSrc {
@@ -41,7 +42,8 @@ struct alignas(64) ConvProblem {
   int tiles_y, tiles_x;
   int ntaps;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
-  int ktot;                 // total K (multiple of 64)
+  int kchunk;               // channels per K block: 64 or 32
+  int ktot;                 // total K (multiple of kchunk)
   const sp_t* w_hi;         // [cout][ktot] K-major
   const sp_t* w_lo;
   const float* bias;        // [cout]

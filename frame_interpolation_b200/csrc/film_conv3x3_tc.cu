@@ -37,19 +37,21 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kBoxRows = (kTileH + 2) * kTileW;     // 144 pixel rows per dx-copy
-constexpr int kAPlane = kBoxRows * 128;             // 18432 B
-constexpr int kAStage = 2 * kAPlane;                // hi + lo = 36864 B
+__host__ __device__ constexpr int a_plane_bytes(int kc) { return kBoxRows * kc * 2; }  // 18432 B (KC = 64)
+__host__ __device__ constexpr int a_stage_bytes(int kc) { return 2 * a_plane_bytes(kc); }
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
 
-__host__ __device__ inline int w_tap_bytes(int bn) { return bn * 128 * 2; }  // [BN x 64] hi + lo
+__host__ __device__ inline int w_tap_bytes(int bn, int kc) { return bn * kc * 2 * 2; }  // [BN x KC] hi + lo
 
-template <int BN>
+template <int BN, int KC>
 __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* __restrict__ prob) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int kWTap = BN * 128 * 2;
+  constexpr int kWTap = BN * KC * 2 * 2;
+  constexpr int kAPlane = a_plane_bytes(KC), kAStage = a_stage_bytes(KC);
+  constexpr int kRowStep = kTileW * KC * 2;  // one tile row of pixels = one swizzle atom (1024 B / 512 B)
   constexpr bool kFused = BN <= 128;
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       // whole weight matrix, once: nkb blocks of [BN x 64] hi then lo
       mbar_expect_tx(tail + 8u * (2 * kMaxRing), (uint32_t)nkb * kWTap);
       for (int kb = 0; kb < nkb; ++kb) {
-        tma_load_2d(w_base + kb * kWTap, tm_w_hi, tail + 8u * (2 * kMaxRing), kb * kChunk, 0);
-        tma_load_2d(w_base + kb * kWTap + kWTap / 2, tm_w_lo, tail + 8u * (2 * kMaxRing), kb * kChunk, 0);
+        tma_load_2d(w_base + kb * kWTap, tm_w_hi, tail + 8u * (2 * kMaxRing), kb * KC, 0);
+        tma_load_2d(w_base + kb * kWTap + kWTap / 2, tm_w_lo, tail + 8u * (2 * kMaxRing), kb * KC, 0);
       }
     }
     __syncwarp();
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
           for (int s = 0; s < nsrc; ++s)
             for (int ch = 0; ch < src_tab[2 * s]; ++ch) {
               // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the 10-px-wide halo
-              const int cc = src_tab[2 * s + 1] + ch * kChunk;
+              const int cc = src_tab[2 * s + 1] + ch * KC;
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 - 1, ny0 - 1, nb);
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 + 1, ny0 - 1, nb);
               tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 - 1, ny0 - 1, nb);
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             if (elect_one()) {
               const uint32_t sa = a_base + st * kAStage, bar = tail + 8u * st;
               mbar_expect_tx(bar, kAStage);
-              tma_load_4d(sa, tm_hi, bar, c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
-              tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * kChunk, x0 + dx - 1, y0 - 1, b);
+              tma_load_4d(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
             }
             __syncwarp();
             ++ia;
@@ -166,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
                 if (elect_one()) {
                   const uint32_t sw = w_base + ws * kWTap, bar = tail + 8u * (2 * kMaxRing + ws);
                   mbar_expect_tx(bar, kWTap);
-                  tma_load_2d(sw, tm_w_hi, bar, kb * kChunk, n0);
-                  tma_load_2d(sw + kWTap / 2, tm_w_lo, bar, kb * kChunk, n0);
+                  tma_load_2d(sw, tm_w_hi, bar, kb * KC, n0);
+                  tma_load_2d(sw + kWTap / 2, tm_w_lo, bar, kb * KC, n0);
                 }
                 __syncwarp();
                 ++iw;
@@ -210,11 +212,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             sw = w_base + ws * kWTap;
           }
           if (elect_one()) {
-            const uint64_t a_hi = make_desc(sa + dy * 1024), a_lo = make_desc(sa + kAPlane + dy * 1024);
-            const uint64_t w_hi = make_desc(sw), w_lo = make_desc(sw + kWTap / 2);
+            const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
+            const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWTap / 2);
             const uint32_t first = (kb == 0) ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < kChunk / 16; ++k) {
+            for (int k = 0; k < KC / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);
               if constexpr (kFused) {
                 umma(d_tmem, a_hi + adv, w_hi + adv, idesc2, k == 0 ? first : 1u);  // N = 2*BN: [W_hi ; W_lo]
@@ -302,9 +304,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
 }
 
 int smem_bytes_for(const ConvProblem& h, int bn) {
-  const int nkb = h.ktot / kChunk;
-  const int w = h.v2_resident ? nkb * w_tap_bytes(bn) : h.v2_nw * w_tap_bytes(bn);
-  return h.v2_na * kAStage + w + kFixedBytes;
+  const int nkb = h.ktot / h.kchunk;
+  const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk) : h.v2_nw * w_tap_bytes(bn, h.kchunk);
+  return h.v2_na * a_stage_bytes(h.kchunk) + w + kFixedBytes;
 }
 
 }  // namespace
@@ -314,9 +316,10 @@ int conv_tc_block_n(int cout);
 // Chooses resident/streamed weights and the ring depths for one 3x3 problem.
 void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int bn = conv_tc_block_n(h.cout);
-  const int nkb = h.ktot / kChunk;
-  const int wtap = w_tap_bytes(bn);
+  const int nkb = h.ktot / h.kchunk;
+  const int wtap = w_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
+  const int kAStage = a_stage_bytes(h.kchunk);
   h.v2_resident = 0;
   if (h.cout <= bn && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;
@@ -334,10 +337,10 @@ void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
 
 cudaError_t conv3x3_tc_configure() {
   cudaError_t e;
-#define FILM_CFG(BN)                                                                                         \
-  e = cudaFuncSetAttribute(k_conv3x3_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);       \
+#define FILM_CFG(BN, KC)                                                                                     \
+  e = cudaFuncSetAttribute(k_conv3x3_tc<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);   \
   if (e != cudaSuccess) return e;
-  FILM_CFG(32) FILM_CFG(64) FILM_CFG(128) FILM_CFG(256)
+  FILM_CFG(32, 64) FILM_CFG(64, 64) FILM_CFG(128, 64) FILM_CFG(256, 64) FILM_CFG(32, 32)
 #undef FILM_CFG
   return cudaSuccess;
 }
@@ -345,11 +348,16 @@ cudaError_t conv3x3_tc_configure() {
 cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
   const int bn = conv_tc_block_n(h.cout);
   const int smem = smem_bytes_for(h, bn);
+  if (h.kchunk == 32) {
+    if (bn != 32) return cudaErrorInvalidValue;  // only the 32 -> 32 flow convs use 32-channel K blocks
+    k_conv3x3_tc<32, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);
+    return cudaGetLastError();
+  }
   switch (bn) {
-    case 256: k_conv3x3_tc<256><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
-    case 128: k_conv3x3_tc<128><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
-    case 64: k_conv3x3_tc<64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
-    default: k_conv3x3_tc<32><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    case 256: k_conv3x3_tc<256, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    case 128: k_conv3x3_tc<128, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    case 64: k_conv3x3_tc<64, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    default: k_conv3x3_tc<32, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
   }
   return cudaGetLastError();
 }

@@ -34,11 +34,10 @@ namespace {
 using namespace tc;
 
 constexpr int kNumThreads = 192;
-constexpr int kABytes = kTileM * kChunk * 2;  // 16 KiB per plane
-
-template <int BN>
+template <int BN, int KC>
 struct TcCfg {
-  static constexpr int kWBytes = BN * kChunk * 2;
+  static constexpr int kABytes = kTileM * KC * 2;  // 16 KiB (KC = 64) or 8 KiB (KC = 32) per plane
+  static constexpr int kWBytes = BN * KC * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
   // Small-N tiles have short K loops and are bound by per-tile serialisation (prologue ->
   // mainloop -> epilogue), not by pipeline depth: give them 2 stages and 2 CTAs per SM so one
@@ -52,9 +51,10 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + BN * 4 + BN * 8 + 16;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob) {
-  using Cfg = TcCfg<BN>;
+template <int BN, int KC>
+__global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob) {
+  using Cfg = TcCfg<BN, KC>;
+  constexpr int kABytes = Cfg::kABytes;
   extern __shared__ uint8_t smem_raw[];
 
   // carve shared memory (1024 B alignment required by SWIZZLE_128B)
@@ -129,11 +129,11 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
           if (elect_one()) {
             const uint32_t sa = base + stage * Cfg::kStageBytes;
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            const int cc = c_off + ch * kChunk;
+            const int cc = c_off + ch * KC;
             tma_load_4d(sa, tm_hi, full_bar(stage), cc, xx, yy, b);
             tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, b);
-            tma_load_2d(sa + 2 * kABytes, tm_w_hi, full_bar(stage), kb * kChunk, n0);
-            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * kChunk, n0);
+            tma_load_2d(sa + 2 * kABytes, tm_w_hi, full_bar(stage), kb * KC, n0);
+            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * KC, n0);
           }
           __syncwarp();
         }
@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = base + stage * Cfg::kStageBytes;
-        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kABytes);
-        const uint64_t w_hi = make_desc(sa + 2 * kABytes), w_lo = make_desc(sa + 2 * kABytes + Cfg::kWBytes);
+        const uint64_t a_hi = make_desc_kc<KC>(sa), a_lo = make_desc_kc<KC>(sa + kABytes);
+        const uint64_t w_hi = make_desc_kc<KC>(sa + 2 * kABytes), w_lo = make_desc_kc<KC>(sa + 2 * kABytes + Cfg::kWBytes);
         const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
-        for (int k = 0; k < kChunk / 16; ++k) {
+        for (int k = 0; k < KC / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 elements x 2 B = 32 B along K
           if constexpr (Cfg::kFused) {
             umma(tmem_base, a_hi + adv, w_hi + adv, idesc2, k == 0 ? first : 1u);  // [W_hi ; W_lo]
@@ -262,10 +262,10 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN>::kMinBlocks) k_conv_tc(
   }
 }
 
-template <int BN>
+template <int BN, int KC>
 cudaError_t launch_bn(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
   dim3 grid(h.B * h.tiles_y * h.tiles_x, (h.cout + BN - 1) / BN);
-  k_conv_tc<BN><<<grid, kNumThreads, TcCfg<BN>::kSmemBytes, st>>>(d_prob);
+  k_conv_tc<BN, KC><<<grid, kNumThreads, TcCfg<BN, KC>::kSmemBytes, st>>>(d_prob);
   return cudaGetLastError();
 }
 
@@ -275,21 +275,27 @@ int conv_tc_block_n(int cout) { return cout >= 256 ? 256 : cout >= 128 ? 128 : c
 
 cudaError_t conv_tc_configure() {
   cudaError_t e;
-#define FILM_CFG(BN)                                                                             \
-  e = cudaFuncSetAttribute(k_conv_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                           TcCfg<BN>::kSmemBytes);                                               \
+#define FILM_CFG(BN, KC)                                                                         \
+  e = cudaFuncSetAttribute(k_conv_tc<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           TcCfg<BN, KC>::kSmemBytes);                                           \
   if (e != cudaSuccess) return e;
-  FILM_CFG(32) FILM_CFG(64) FILM_CFG(128) FILM_CFG(256)
+  FILM_CFG(32, 64) FILM_CFG(64, 64) FILM_CFG(128, 64) FILM_CFG(256, 64) FILM_CFG(32, 32) FILM_CFG(64, 32)
 #undef FILM_CFG
   return cudaSuccess;
 }
 
 cudaError_t launch_conv_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
-  switch (conv_tc_block_n(h.cout)) {
-    case 256: return launch_bn<256>(d_prob, h, st);
-    case 128: return launch_bn<128>(d_prob, h, st);
-    case 64: return launch_bn<64>(d_prob, h, st);
-    default: return launch_bn<32>(d_prob, h, st);
+  const int bn = conv_tc_block_n(h.cout);
+  if (h.kchunk == 32) {
+    if (bn == 64) return launch_bn<64, 32>(d_prob, h, st);
+    if (bn == 32) return launch_bn<32, 32>(d_prob, h, st);
+    return cudaErrorInvalidValue;  // 32-channel K blocks are only instantiated for Cout <= 64
+  }
+  switch (bn) {
+    case 256: return launch_bn<256, 64>(d_prob, h, st);
+    case 128: return launch_bn<128, 64>(d_prob, h, st);
+    case 64: return launch_bn<64, 64>(d_prob, h, st);
+    default: return launch_bn<32, 64>(d_prob, h, st);
   }
 }
 

@@ -142,7 +142,8 @@ struct PackedConv {
   sp_t* w_lo = nullptr;
   float* bias = nullptr;
   int cout = 0, ktot = 0, cin_ref = 0;
-  std::vector<int> src_chunks;  // 64-channel chunks per source
+  int kchunk = kChunk;          // channels per K block (64, or 32 for the 32-channel layers)
+  std::vector<int> src_chunks;  // K-block chunks per source
   int ntaps = 0;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
 };
@@ -156,11 +157,12 @@ struct TapSpec {
 // K order = (source, 64-chunk, tap, channel-in-chunk), matching the kernels' K loop.
 static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
                             const std::vector<std::vector<int>>& src_maps,
-                            const std::vector<TapSpec>& taps, std::vector<void*>& allocs) {
+                            const std::vector<TapSpec>& taps, std::vector<void*>& allocs, int chunk = kChunk) {
   const int kw = kernel.dims[1], cin = kernel.dims[2], cout = kernel.dims[3];
   PackedConv pc;
   pc.cout = cout;
   pc.cin_ref = cin;
+  pc.kchunk = chunk;
   pc.ntaps = (int)taps.size();
   for (size_t t = 0; t < taps.size(); ++t) {
     pc.tap_dy[t] = taps[t].dy;
@@ -168,19 +170,19 @@ static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
   }
   int ktot = 0;
   for (auto& sm : src_maps) {
-    if (sm.size() % kChunk) throw Error{FILM_ERR_WEIGHTS, "source channel map not a multiple of 64"};
-    pc.src_chunks.push_back((int)sm.size() / kChunk);
+    if (sm.size() % chunk) throw Error{FILM_ERR_WEIGHTS, "source channel map not a multiple of the K chunk"};
+    pc.src_chunks.push_back((int)sm.size() / chunk);
     ktot += (int)sm.size() * (int)taps.size();
   }
   pc.ktot = ktot;
   std::vector<uint16_t> hi((size_t)cout * ktot), lo((size_t)cout * ktot);
   int kbase = 0;
   for (auto& sm : src_maps) {
-    const int nchunk = (int)sm.size() / kChunk;
+    const int nchunk = (int)sm.size() / chunk;
     for (int ch = 0; ch < nchunk; ++ch) {
-      for (size_t t = 0; t < taps.size(); ++t, kbase += kChunk) {
-        for (int c = 0; c < kChunk; ++c) {
-          const int ref = sm[ch * kChunk + c];
+      for (size_t t = 0; t < taps.size(); ++t, kbase += chunk) {
+        for (int c = 0; c < chunk; ++c) {
+          const int ref = sm[ch * chunk + c];
           for (int n = 0; n < cout; ++n) {
             float w = 0.f;
             if (ref >= 0) {
@@ -276,6 +278,14 @@ struct Model {
     const std::string fe_pre = "feat_net/sub_extractor/cfeat_conv_";
     conv0_w = upload(get_tensor(w, fe_pre + "0/kernel", {3, 3, 3, 64}));
     conv0_b = upload(get_tensor(w, fe_pre + "0/bias", {64}));
+    {
+      // tensor-core version of cfeat_conv_0: the HWIO kernel [3][3][3][64] flattened to a 1x1 conv over
+      // the 27 im2col channels (k = (ky*3+kx)*3 + ci, film_kernels.cu k_im2col3x3), one 32-channel K block
+      HostTensor k0 = get_tensor(w, fe_pre + "0/kernel", {3, 3, 3, 64});
+      k0.dims = {1, 1, 27, 64};
+      fe[0] = pack_conv(k0, get_tensor(w, fe_pre + "0/bias", {64}), {iota_map(0, 27, 32)},
+                        {TapSpec{0, 0, {{0, 0}}}}, allocs, 32);
+    }
     int cin = 64;
     for (int k = 1; k < 8; ++k) {
       const int c = kFilters << (k / 2);
@@ -290,13 +300,14 @@ struct Model {
       flow[p][0] = pack_conv(get_tensor(w, pre + "0/kernel", {3, 3, 2 * C, nf}),
                              get_tensor(w, pre + "0/bias", {nf}),
                              {iota_map(0, C, C), iota_map(C, C, C)}, taps_3x3(), allocs);
+      const int kc = nf < kChunk ? 32 : kChunk;  // the 32-filter predictor uses 32-channel K blocks
       for (int k = 1; k < 3; ++k)
         flow[p][k] = pack_conv(get_tensor(w, pre + std::to_string(k) + "/kernel", {3, 3, nf, nf}),
                                get_tensor(w, pre + std::to_string(k) + "/bias", {nf}),
-                               {iota_map(0, nf, round_up(nf, kChunk))}, taps_3x3(), allocs);
+                               {iota_map(0, nf, round_up(nf, kc))}, taps_3x3(), allocs, kc);
       flow_c3[p] = pack_conv(get_tensor(w, pre + "3/kernel", {1, 1, nf, nf / 2}),
-                             get_tensor(w, pre + "3/bias", {nf / 2}), {iota_map(0, nf, round_up(nf, kChunk))},
-                             {TapSpec{0, 0, {{0, 0}}}}, allocs);
+                             get_tensor(w, pre + "3/bias", {nf / 2}), {iota_map(0, nf, round_up(nf, kc))},
+                             {TapSpec{0, 0, {{0, 0}}}}, allocs, kc);
       flow_w3[p] = upload(get_tensor(w, pre + "3/kernel", {1, 1, nf, nf / 2}));
       flow_b3[p] = upload(get_tensor(w, pre + "3/bias", {nf / 2}));
       flow_w4[p] = upload(get_tensor(w, pre + "4/kernel", {1, 1, nf / 2, 2}));
@@ -361,23 +372,23 @@ static const CUtensorMapDataType kTmType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 static const CUtensorMapDataType kTmType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 #endif
 
-static void make_act_map(CUtensorMap* tm, const sp_t* base, int B, int H, int W, int C, int th, int tw) {
+static void make_act_map(CUtensorMap* tm, const sp_t* base, int B, int H, int W, int C, int th, int tw, int kc) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tw, (cuuint32_t)th, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = get_encode_fn()(tm, kTmType, 4, (void*)base, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error{FILM_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)};
 }
-static void make_w_map(CUtensorMap* tm, const sp_t* base, int cout, int ktot, int bn) {
+static void make_w_map(CUtensorMap* tm, const sp_t* base, int cout, int ktot, int bn, int kc) {
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
   cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)bn};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(tm, kTmType, 2, (void*)base, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error{FILM_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)};
 }
@@ -497,7 +508,10 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.H = s0->H;
   cp.W = s0->W;
   // 3x3 SAME convs with a unit-stride destination run on the persistent tap-reuse kernel
-  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1;
+  const int kc = pc.kchunk;
+  cp.kchunk = kc;
+  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1 &&
+                  (kc == kChunk || pc.cout <= 32);
   int box_h, box_w;
   if (v2) {
     cp.tile_h = 16;
@@ -519,9 +533,9 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     cp.src[s].C = b->C;
     cp.src[s].c_off = sources[s].c_off;
     cp.src[s].nchunk = pc.src_chunks[s];
-    if (sources[s].c_off + pc.src_chunks[s] * kChunk > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
-    make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w);
-    make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w);
+    if (sources[s].c_off + pc.src_chunks[s] * kc > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
+    make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w, kc);
+    make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w, kc);
   }
   cp.ntaps = pc.ntaps;
   for (int t = 0; t < pc.ntaps; ++t) {
@@ -535,8 +549,8 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.cout = pc.cout;
   cp.act = act;
   const int bn = conv_tc_block_n(pc.cout);
-  make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn);
-  make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn);
+  make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn, kc);
+  make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn, kc);
   if (out) {
     cp.out_hi = out->hi;
     cp.out_lo = out->lo;
@@ -635,7 +649,16 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     for (int j = 0; j < depth; ++j) {
       const int r = i + j, c = kFilters << j;
       SplitBuf* t1 = P.split(2, Hs[r], Ws[r], c);
-      if (j == 0) {
+      if (j == 0 && P.conv_impl == 0) {
+        // cfeat_conv_0 on the tensor cores: im2col-lite (27 -> 32 channels) + a 1x1 conv, K = 32
+        const float* im = img[i];
+        const int hh = Hs[r], ww = Ws[r];
+        SplitBuf* col = P.split(2, hh, ww, 32);
+        P.add_op(2, "fe_im2col@L" + std::to_string(r),
+                 [=](cudaStream_t st) { return launch_im2col3x3(im, 2, hh, ww, col->hi, col->lo, st); }, 0,
+                 2.0 * hh * ww * (12 + 128.0));
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe[0], {{col, 0}}, 1, t1, 0);
+      } else if (j == 0) {
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
         const float *w0 = M.conv0_w, *b0 = M.conv0_b;
@@ -713,7 +736,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       P.warp_bytes += 2.0 * hh * ww * (double)C * 8.0;
       second = warped;
     }
-    const int cpad = round_up(nf, kChunk);
+    const int cpad = round_up(nf, nf < kChunk ? 32 : kChunk);
     SplitBuf* c0 = P.split(2, hh, ww, cpad);
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);

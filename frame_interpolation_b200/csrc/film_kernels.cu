@@ -123,6 +123,47 @@ cudaError_t launch_conv0_c3(const float* img, int B, int H, int W, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// im2col-lite for cfeat_conv_0 (tensor-core path): out[p][k] = img[p + tap(k)][ci(k)],
+// k = (ky*3 + kx)*3 + ci for k < 27, zero for 27 <= k < 32 and outside the image (SAME padding).
+// The 3 -> 64 conv then is a 1x1 tensor-core conv with one 32-channel K block.
+// 4 threads per pixel, 8 channels (one 128-bit store per plane) each.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_im2col3x3(const float* __restrict__ img, int B, int H, int W,
+                                                   sp_t* __restrict__ out_hi, sp_t* __restrict__ out_lo) {
+  const int64_t n = (int64_t)B * H * W * 4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = (int)(i & 3);
+  const int64_t p = i >> 2;
+  const int x = (int)(p % W);
+  const int64_t q = p / W;
+  const int y = (int)(q % H);
+  const int b = (int)(q / H);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float val = 0.f;
+    if (k < 27) {
+      const int tap = k / 3, ci = k - tap * 3;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(img + (((int64_t)b * H + yy) * W + xx) * 3 + ci);
+    }
+    v[j] = val;
+  }
+  uint4 h, l;
+  pack8(v, h, l);
+  *reinterpret_cast<uint4*>(out_hi + p * 32 + g * 8) = h;
+  *reinterpret_cast<uint4*>(out_lo + p * 32 + g * 8) = l;
+}
+
+cudaError_t launch_im2col3x3(const float* img, int B, int H, int W, sp_t* out_hi, sp_t* out_lo, cudaStream_t st) {
+  int64_t n = (int64_t)B * H * W * 4;
+  k_im2col3x3<<<cdiv(n, 256), 256, 0, st>>>(img, B, H, W, out_hi, out_lo);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // feature_extractor.py:138-146  avg-pool of a channel slice of a split tensor
 // ------------------------------------------------------------------------------------------
 __global__ void k_act_pool(const sp_t* __restrict__ in_hi, const sp_t* __restrict__ in_lo, int in_C,
@@ -532,14 +573,15 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvProblem* __restrict
     pb = (int)(q / P.H);
   }
   int kb = 0;
+  const int KC = P.kchunk;
   for (int s = 0; s < P.nsrc; ++s) {
     const ConvSrc& S = P.src[s];
     for (int ch = 0; ch < S.nchunk; ++ch) {
       for (int t = 0; t < P.ntaps; ++t, ++kb) {
         const int yy = py + P.tap_dy[t], xx = px + P.tap_dx[t];
         const bool ok = pm_ok && yy >= 0 && yy < P.H && xx >= 0 && xx < P.W;
-        const int64_t abase = (((int64_t)pb * P.H + yy) * P.W + xx) * S.C + S.c_off + ch * kChunk;
-        for (int k16 = 0; k16 < kChunk; k16 += 16) {
+        const int64_t abase = (((int64_t)pb * P.H + yy) * P.W + xx) * S.C + S.c_off + ch * KC;
+        for (int k16 = 0; k16 < KC; k16 += 16) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float v = 0.f;
@@ -553,7 +595,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvProblem* __restrict
             for (int e = 0; e < 4; ++e) {
               float v = 0.f;
               if (n < P.cout) {
-                int64_t wi = (int64_t)n * P.ktot + (int64_t)kb * kChunk + k16 + lk + e;
+                int64_t wi = (int64_t)n * P.ktot + (int64_t)kb * KC + k16 + lk + e;
                 v = sp_to_float(P.w_hi[wi]) + sp_to_float(P.w_lo[wi]);
               }
               Ws[lk + e][lm] = v;

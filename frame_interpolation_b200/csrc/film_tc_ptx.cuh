@@ -77,6 +77,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+// Same for a K chunk of KC channels per row: KC = 64 -> 128-byte rows, SWIZZLE_128B (type 2),
+// 8-row atom = 1024 B; KC = 32 -> 64-byte rows, SWIZZLE_64B (type 4), 8-row atom = 512 B.
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc_kc(uint32_t saddr) {
+  constexpr uint64_t kType = (KC == 64) ? 2 : 4;
+  constexpr uint64_t kSbo = (KC == 64) ? 1024 : 512;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(kSbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= kType << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format=F32 [4,6),
 // a_format [7,10), b_format [10,13) (0 = F16, 1 = BF16), K-major A and B, N>>3 [17,23), M>>4 [24,29).
 template <int BN>
