@@ -68,6 +68,12 @@ struct alignas(64) ConvProblem {
   int v2_resident;        // 1: all W_hi/W_lo K blocks stay in shared memory for the CTA's lifetime
   int v2_na, v2_nw;       // activation-ring / weight-ring stages
   int v2_grid;            // persistent CTAs
+  // optional fused 2x2/2 average pool of the (activated, fp32) output tile, written as a second
+  // split tensor [B][H/2][W/2][pool_C] (feature_extractor.py:138-146); null = off
+  sp_t* pool_hi;
+  sp_t* pool_lo;
+  int pool_C;
+  int group;              // generic kernel: number of consecutive problems launched as grid.z
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)
@@ -76,6 +82,7 @@ cudaError_t launch_conv_simt(const ConvProblem* d_prob, const ConvProblem& h_pro
 cudaError_t conv_tc_configure();  // cudaFuncSetAttribute for all instantiations
 // persistent 3x3 variant: fills the v2_* fields of `h_prob` (call before uploading the problem)
 void conv3x3_tc_plan(ConvProblem& h_prob, int num_sms);
+void conv3x3_tc_pick_tile(int H, int W, int B, int cout, int num_sms, int& tile_h, int& tile_w);
 cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
 cudaError_t conv3x3_tc_configure();
 

@@ -35,10 +35,10 @@ using namespace tc;
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kTileH = 16, kTileW = 8;
-constexpr int kBoxRows = (kTileH + 2) * kTileW;     // 144 pixel rows per dx-copy
-__host__ __device__ constexpr int a_plane_bytes(int kc) { return kBoxRows * kc * 2; }  // 18432 B (KC = 64)
-__host__ __device__ constexpr int a_stage_bytes(int kc) { return 2 * a_plane_bytes(kc); }
+// Tile shapes: tile_w must be a multiple of 8 pixels (one swizzle atom) and tile_h * tile_w = 128.
+// 16x8 has the smallest halo (18/16); 8x16 and 4x32 exist to avoid wave quantisation on small levels.
+__host__ __device__ constexpr int a_plane_bytes(int kc, int th, int tw) { return (th + 2) * tw * kc * 2; }
+__host__ __device__ constexpr int a_stage_bytes(int kc, int th, int tw) { return 2 * a_plane_bytes(kc, th, tw); }
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
@@ -50,8 +50,9 @@ template <int BN, int KC>
 __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* __restrict__ prob) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int kWTap = BN * KC * 2 * 2;
-  constexpr int kAPlane = a_plane_bytes(KC), kAStage = a_stage_bytes(KC);
-  constexpr int kRowStep = kTileW * KC * 2;  // one tile row of pixels = one swizzle atom (1024 B / 512 B)
+  const int kTileH = prob->tile_h, kTileW = prob->tile_w;
+  const int kAPlane = a_plane_bytes(KC, kTileH, kTileW), kAStage = a_stage_bytes(KC, kTileH, kTileW);
+  const int kRowStep = kTileW * KC * 2;  // one tile row of pixels = tile_w/8 swizzle atoms
   constexpr bool kFused = BN <= 128;
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
           const int ny0 = (nrem / tiles_x) * kTileH, nx0 = (nrem % tiles_x) * kTileW;
           for (int s = 0; s < nsrc; ++s)
             for (int ch = 0; ch < src_tab[2 * s]; ++ch) {
-              // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the 10-px-wide halo
+              // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the (tile_w + 2)-px-wide halo
               const int cc = src_tab[2 * s + 1] + ch * KC;
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 - 1, ny0 - 1, nb);
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 + 1, ny0 - 1, nb);
@@ -246,6 +247,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     const int out_c_off = prob->out_c_off, act = prob->act;
     sp_t* const out_hi = prob->out_hi;
     sp_t* const out_lo = prob->out_lo;
+    // fused 2x2/2 average pool: only for 16x8 tiles (a warp's 32 lanes = 4 tile rows x 8 columns, so
+    // the 2x2 partners of lane l are l^1, l^8, l^9 -> three warp shuffles on the fp32 values)
+    sp_t* const pool_hi = prob->pool_hi;
+    sp_t* const pool_lo = prob->pool_lo;
+    const int pool_C = prob->pool_C;
+    const bool do_pool = pool_hi != nullptr;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
@@ -273,19 +280,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         } else {
           tmem_ld_wait();
         }
-        if (valid) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float f[8];
+        for (int g = 0; g < 2; ++g) {
+          float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 16 + g * 8 + j];
-              f[j] = act ? leaky(x) : x;
-            }
+          for (int j = 0; j < 8; ++j) {
+            float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 16 + g * 8 + j];
+            f[j] = act ? leaky(x) : x;
+          }
+          if (valid) {
             uint4 h, l;
             pack8(f, h, l);
             *reinterpret_cast<uint4*>(oh + cc * 16 + g * 8) = h;
             *reinterpret_cast<uint4*>(ol + cc * 16 + g * 8) = l;
+          }
+          if (do_pool) {
+            float pf[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
+              pf[j] = (a + __shfl_xor_sync(0xffffffffu, a, 8)) * 0.25f;
+            }
+            // lanes with even tile row and even tile column own the pooled pixel (H, W are even)
+            if (valid && !(lane & 1) && !(lane & 8)) {
+              const int64_t ppix = ((int64_t)b * (out_H >> 1) + (py >> 1)) * (out_W >> 1) + (px >> 1);
+              uint4 h, l;
+              pack8(pf, h, l);
+              *reinterpret_cast<uint4*>(pool_hi + ppix * pool_C + n0 + cc * 16 + g * 8) = h;
+              *reinterpret_cast<uint4*>(pool_lo + ppix * pool_C + n0 + cc * 16 + g * 8) = l;
+            }
           }
         }
       }
@@ -306,12 +329,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
 int smem_bytes_for(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
   const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk) : h.v2_nw * w_tap_bytes(bn, h.kchunk);
-  return h.v2_na * a_stage_bytes(h.kchunk) + w + kFixedBytes;
+  return h.v2_na * a_stage_bytes(h.kchunk, h.tile_h, h.tile_w) + w + kFixedBytes;
 }
 
 }  // namespace
 
 int conv_tc_block_n(int cout);
+
+// Tile shape: fewest waves over the SMs first (a 151st tile costs a whole extra wave on a small
+// level), then the smallest halo.  16x8 is required by the fused pool.
+void conv3x3_tc_pick_tile(int H, int W, int B, int cout, int num_sms, int& tile_h, int& tile_w) {
+  static const int cand[3][2] = {{16, 8}, {8, 16}, {4, 32}};
+  const int bn = conv_tc_block_n(cout);
+  const int n_nt = (cout + bn - 1) / bn;
+  double best = 1e30;
+  for (auto& c : cand) {
+    const long tiles = (long)B * ((H + c[0] - 1) / c[0]) * ((W + c[1] - 1) / c[1]) * n_nt;
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const double cost = (double)waves * (c[0] + 2.0) / c[0] * (1.0 + 1e-3 * (c[1] / 8));
+    if (cost < best) {
+      best = cost;
+      tile_h = c[0];
+      tile_w = c[1];
+    }
+  }
+}
 
 // Chooses resident/streamed weights and the ring depths for one 3x3 problem.
 void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
@@ -319,7 +361,7 @@ void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int nkb = h.ktot / h.kchunk;
   const int wtap = w_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
-  const int kAStage = a_stage_bytes(h.kchunk);
+  const int kAStage = a_stage_bytes(h.kchunk, h.tile_h, h.tile_w);
   h.v2_resident = 0;
   if (h.cout <= bn && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;

@@ -52,8 +52,11 @@ struct TcCfg {
 };
 
 template <int BN, int KC>
-__global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob) {
+__global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv_tc(const ConvProblem* __restrict__ prob_base) {
   using Cfg = TcCfg<BN, KC>;
+  // grid.z selects one of `group` consecutive problems with identical grids (the four parity classes
+  // of the NN-upsample + 2x2 conv are one launch)
+  const ConvProblem* __restrict__ prob = prob_base + blockIdx.z;
   constexpr int kABytes = Cfg::kABytes;
   extern __shared__ uint8_t smem_raw[];
 
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
 
 template <int BN, int KC>
 cudaError_t launch_bn(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
-  dim3 grid(h.B * h.tiles_y * h.tiles_x, (h.cout + BN - 1) / BN);
+  dim3 grid(h.B * h.tiles_y * h.tiles_x, (h.cout + BN - 1) / BN, h.group > 1 ? h.group : 1);
   k_conv_tc<BN, KC><<<grid, kNumThreads, TcCfg<BN, KC>::kSmemBytes, st>>>(d_prob);
   return cudaGetLastError();
 }

@@ -498,7 +498,8 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 // Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
 static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
                        const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
-                       int sy = 1, int sx = 1, int oy = 0, int ox = 0) {
+                       int sy = 1, int sx = 1, int oy = 0, int ox = 0, const SplitBuf* pool_out = nullptr,
+                       bool no_op = false) {
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
   const SplitBuf* s0 = sources[0].buf;
@@ -514,10 +515,14 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
                   (kc == kChunk || pc.cout <= 32);
   int box_h, box_w;
   if (v2) {
-    cp.tile_h = 16;
-    cp.tile_w = 8;
-    box_h = 18;
-    box_w = 8;
+    if (pool_out) {
+      cp.tile_h = 16;  // the fused pool maps 2x2 partners to lanes l^1 / l^8 of a 16x8 tile
+      cp.tile_w = 8;
+    } else {
+      conv3x3_tc_pick_tile(cp.H, cp.W, cp.B, pc.cout, P.num_sms, cp.tile_h, cp.tile_w);
+    }
+    box_h = cp.tile_h + 2;
+    box_w = cp.tile_w;
   } else {
     pick_tile(cp.H, cp.W, cp.tile_h, cp.tile_w);
     box_h = cp.tile_h;
@@ -568,9 +573,20 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.out_oy = oy;
   cp.out_ox = ox;
   if (out && (out->B != cp.B || out_c_off + pc.cout > out->C)) throw Error{FILM_ERR_ARG, "conv destination mismatch"};
+  if (pool_out) {
+    if (!v2) throw Error{FILM_ERR_UNSUPPORTED, "fused pool needs the persistent 3x3 kernel"};
+    cp.pool_hi = pool_out->hi;
+    cp.pool_lo = pool_out->lo;
+    cp.pool_C = pool_out->C;
+  }
+  cp.group = 1;
   if (v2) conv3x3_tc_plan(cp, P.num_sms);
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
+  // issued tensor-core work: 3 passes over the padded K and the padded tile grid
+  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
+                 (double)(((pc.cout + bn - 1) / bn) * bn);
+  if (no_op) return idx;  // the caller launches this problem as part of a group
   Plan* pp = &P;
   const int impl = P.conv_impl;
   P.add_op(0, tag, [pp, idx, impl, v2](cudaStream_t st) {
@@ -578,9 +594,6 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     return v2 ? launch_conv3x3_tc(pp->d_probs + idx, pp->h_probs[idx], st)
               : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
   }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W);
-  // issued tensor-core work: 3 passes over the padded K and the padded tile grid
-  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
-                 (double)(((pc.cout + bn - 1) / bn) * bn);
   return idx;
 }
 
@@ -672,12 +685,17 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       }
       // second conv of the pair writes straight into the cascaded feature tensor slice
       // (replaces the tf.concat at feature_extractor.py:191)
+      SplitBuf* pool_target = nullptr;
+      const bool fuse_pool = (j < depth - 1) && P.conv_impl == 0 && P.conv3x3_v2;
+      if (j < depth - 1) pool_target = P.split(2, Hs[r + 1], Ws[r + 1], c);
       add_conv(P, "fe_conv" + std::to_string(2 * j + 1) + "@L" + std::to_string(r), 9.0 * c * c, M.fe[2 * j + 1],
-               {{t1, 0}}, 1, feat[r], slice_off[j]);
+               {{t1, 0}}, 1, feat[r], slice_off[j], 1, 1, 0, 0, fuse_pool ? pool_target : nullptr);
       tok_feat[i][j] = P.new_token();
       P.signal_last(tok_feat[i][j]);
-      if (j < depth - 1) {
-        pooled = P.split(2, Hs[r + 1], Ws[r + 1], c);
+      if (fuse_pool) {
+        pooled = pool_target;  // written by the conv epilogue (feature_extractor.py:138-146 fused)
+      } else if (j < depth - 1) {
+        pooled = pool_target;
         const SplitBuf* f = feat[r];
         const SplitBuf* po = pooled;
         const int so = slice_off[j];
@@ -817,10 +835,26 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       up_src = {{batch_view(wf[i + 1], 0), 0}, {batch_view(wf[i + 1], 1), 0}, {side[i + 1], 0}};
     else
       up_src = {{net, 0}};
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px)
-        add_conv(P, "fusion_up" + std::to_string(py * 2 + px) + "@L" + std::to_string(i),
-                 4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
+    if (P.conv_impl == 0) {
+      // the four parity classes share the grid: ONE launch, grid.z = class
+      size_t first = 0;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const size_t ci = add_conv(P, "", 0, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px, nullptr, true);
+          if (py == 0 && px == 0) first = ci;
+        }
+      P.h_probs[first].group = 4;
+      Plan* pq = &P;
+      const double fl = 2.0 * 16.0 * M.fus_up[i][0].cin_ref * nf * (double)Hs[i + 1] * Ws[i + 1];
+      P.add_op(0, "fusion_up@L" + std::to_string(i), [pq, first](cudaStream_t st) {
+        return launch_conv_tc(pq->d_probs + first, pq->h_probs[first], st);
+      }, fl);
+    } else {
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          add_conv(P, "fusion_up" + std::to_string(py * 2 + px) + "@L" + std::to_string(i),
+                   4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
+    }
     SplitBuf* f1 = P.split(1, hh, ww, cpad);
     SplitBuf* f2 = P.split(1, hh, ww, cpad);
     add_conv(P, "fusion_conv1@L" + std::to_string(i), 9.0 * M.fus_c1[i].cin_ref * nf, M.fus_c1[i],
@@ -1211,6 +1245,62 @@ int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, con
         ms_d2h += t;
       }
     fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
+    return FILM_OK;
+  } catch (const Error& e) {
+    return fail(h, e);
+  }
+}
+
+int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W, int align,
+                               int times_to_interpolate, float* out) {
+  if (!h) return FILM_ERR_ARG;
+  try {
+    check_frame_args(frame0, frame1, out, 1, H, W);
+    if (times_to_interpolate < 0 || times_to_interpolate > 10) throw Error{FILM_ERR_ARG, "times_to_interpolate must be in [0, 10]"};
+    FILM_CUDA(cudaSetDevice(h->device));
+    (void)cudaGetLastError();
+    Plan* P = get_plan(h, H, W, align);
+    const int n = (1 << times_to_interpolate) + 1;
+    const size_t frame = (size_t)H * W * 3 * sizeof(float);
+    float* seq = nullptr;
+    FILM_CUDA(cudaMalloc(&seq, frame * n));
+    cudaError_t e = cudaSuccess;
+    auto slot = [&](int i) { return (float*)((char*)seq + frame * i); };
+    auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    chk(cudaEventRecord(h->ev[0], h->stream));
+    chk(cudaMemcpyAsync(slot(0), frame0, frame, cudaMemcpyHostToDevice, h->stream));
+    chk(cudaMemcpyAsync(slot(n - 1), frame1, frame, cudaMemcpyHostToDevice, h->stream));
+    chk(cudaEventRecord(h->ev[1], h->stream));
+    // level-synchronous traversal of the binary tree of eval/util.py:62-91; every mid-frame stays in HBM
+    for (int step = (n - 1) / 2; step >= 1 && e == cudaSuccess; step /= 2) {
+      for (int i = step; i < n - 1 && e == cudaSuccess; i += 2 * step) {
+        chk(cudaMemcpyAsync(P->xin, slot(i - step), frame, cudaMemcpyDeviceToDevice, h->stream));
+        chk(cudaMemcpyAsync((char*)P->xin + frame, slot(i + step), frame, cudaMemcpyDeviceToDevice, h->stream));
+        if (e == cudaSuccess) {
+          try {
+            run_plan(h, P, h->stream);
+          } catch (const Error& err) {
+            cudaFree(seq);
+            throw;
+          }
+        }
+        chk(cudaMemcpyAsync(slot(i), P->xout, frame, cudaMemcpyDeviceToDevice, h->stream));
+      }
+    }
+    chk(cudaEventRecord(h->ev[2], h->stream));
+    chk(cudaMemcpyAsync(out, seq, frame * n, cudaMemcpyDeviceToHost, h->stream));
+    chk(cudaEventRecord(h->ev[3], h->stream));
+    chk(cudaStreamSynchronize(h->stream));
+    float t_h2d = 0, t_net = 0, t_d2h = 0;
+    if (e == cudaSuccess) {
+      cudaEventElapsedTime(&t_h2d, h->ev[0], h->ev[1]);
+      cudaEventElapsedTime(&t_net, h->ev[1], h->ev[2]);
+      cudaEventElapsedTime(&t_d2h, h->ev[2], h->ev[3]);
+    }
+    cudaFree(seq);
+    FILM_CUDA(e);
+    fill_profile(h, P, t_net, t_h2d, t_d2h);
+    h->prof.kernel_launches = (int64_t)P->ops.size() * (n - 2);
     return FILM_OK;
   } catch (const Error& e) {
     return fail(h, e);

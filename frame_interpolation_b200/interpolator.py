@@ -151,6 +151,27 @@ class Interpolator:
                                                C.c_void_p(d_out), out_pitch, C.c_void_p(stream))
         self._check(st)
 
+    def interpolate_recursively(self, frame0: np.ndarray, frame1: np.ndarray,
+                                times_to_interpolate: int) -> np.ndarray:
+        """All frames between two (H, W, 3) frames, end points included, in display order:
+        (2**times + 1, H, W, 3). The recursion of eval/util.py:62-91 runs with every
+        intermediate frame resident on the device (film_interpolate_recursive). Only for the
+        untiled path; bit-identical to recursive calls of `__call__`."""
+        if self._align is not None:
+            assert self._align > 0, 'align must be a positive number.'
+        assert self._block_shape is None or np.prod(self._block_shape) <= 1, \
+            "device-resident recursion is the untiled path"
+        f0 = np.ascontiguousarray(frame0, dtype=np.float32)
+        f1 = np.ascontiguousarray(frame1, dtype=np.float32)
+        assert f0.ndim == 3 and f0.shape == f1.shape and f0.shape[-1] == 3, "expected two (H, W, 3) frames"
+        h, w, _ = f0.shape
+        n = (1 << int(times_to_interpolate)) + 1
+        out = np.empty((n, h, w, 3), np.float32)
+        st = self._lib.film_interpolate_recursive(self._handle, _fptr(f0), _fptr(f1), h, w,
+                                                  int(self._align or 0), int(times_to_interpolate), _fptr(out))
+        self._check(st)
+        return out
+
     def synchronize(self) -> None:
         self._check(self._lib.film_synchronize(self._handle))
 

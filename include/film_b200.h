@@ -99,6 +99,14 @@ FILM_API int film_interpolate_device(film_handle* h, const float* d_x0, const fl
                             int B, int H, int W, int64_t in_pitch, int align,
                             float* d_out, int64_t out_pitch, void* cuda_stream);
 
+/* Recursive mid-point interpolation between two (H, W, 3) host frames, the whole binary tree of
+ * eval/util.py:62-91 (`_recursive_generator`) evaluated with every intermediate frame resident in
+ * HBM: 2 uploads, 2^times - 1 network calls, 1 download.  `out` receives 2^times + 1 frames in
+ * display order INCLUDING both end points (what interpolate_recursively_from_memory yields for one
+ * pair, eval/util.py:125-153).  Results are bit-identical to calling film_interpolate recursively. */
+FILM_API int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W,
+                                        int align, int times_to_interpolate, float* out);
+
 FILM_API int film_synchronize(film_handle* h);
 
 /* Fills *out with statistics of the last call on this handle. */

@@ -216,3 +216,43 @@ def test_full_size_1080p_parity_and_properties(synthetic_weights):
     assert err < 5e-4, err
     assert psnr(out, ref) > 80.0
     eng.close()
+
+
+def test_device_resident_recursion_equals_host_recursion(engine):
+    """film_interpolate_recursive (frames stay in HBM) vs eval/util.py-style recursion through __call__."""
+    from frame_interpolation_b200 import eval_util
+    x0, x1 = synthetic.frame_pair(90, 160, seed=21, n_waves=6)
+    seq = engine.interpolate_recursively(x0[0], x1[0], 3)
+    assert seq.shape == (9, 90, 160, 3)
+
+    def rec(a, b, n):
+        if n == 0:
+            return [a]
+        m = engine(a[None], b[None], DT)[0]
+        return rec(a, m, n - 1) + rec(m, b, n - 1)
+    want = rec(x0[0], x1[0], 3) + [x1[0]]
+    for got, ref in zip(seq, want):
+        np.testing.assert_array_equal(got, ref)
+    # the scheduling helper picks the device-resident path for the engine and yields the same frames
+    frames = list(eval_util.interpolate_recursively_from_memory([x0[0], x1[0], x0[0]], 2, engine))
+    assert len(frames) == 2 * 4 + 1
+    np.testing.assert_array_equal(frames[2], engine(x0, x1, DT)[0])
+    np.testing.assert_array_equal(frames[4], x1[0])
+
+
+def test_cli_end_to_end(tmp_path, synthetic_weights):
+    from frame_interpolation_b200 import eval_util, interpolator_cli, interpolator_test
+    d = tmp_path / "scene"
+    d.mkdir()
+    x0, x1 = synthetic.frame_pair(96, 128, seed=5, n_waves=6)
+    eval_util.write_image(str(d / "a1.png"), x0[0])
+    eval_util.write_image(str(d / "a2.png"), x1[0])
+    assert interpolator_cli.main(["--pattern", str(tmp_path / "*"), "--model_path", synthetic_weights[0],
+                                  "--times_to_interpolate", "2", "--block_height", "2", "--block_width", "2"]) == 0
+    out = sorted(os.listdir(d / "interpolated_frames"))
+    assert out == [f"frame_{i:03d}.png" for i in range(5)]
+    mid = eval_util.read_image(str(d / "interpolated_frames" / "frame_002.png"))
+    assert interpolator_test.main(["--frame1", str(d / "a1.png"), "--frame2", str(d / "a2.png"), "--model_path",
+                                   synthetic_weights[0], "--block_height", "2", "--block_width", "2",
+                                   "--output_frame", str(tmp_path / "mid.png")]) == 0
+    np.testing.assert_array_equal(mid, eval_util.read_image(str(tmp_path / "mid.png")))
