@@ -35,6 +35,8 @@ struct alignas(64) ConvProblem {
   CUtensorMap tm_a_lo[kMaxSrc];
   CUtensorMap tm_w_hi;
   CUtensorMap tm_w_lo;
+  CUtensorMap tm_w_hi_half;  // box [BN/2 x KC]: CTA-pair kernel, each CTA loads half of the weight rows
+  CUtensorMap tm_w_lo_half;
   ConvSrc src[kMaxSrc];
   int nsrc;
   int B, H, W;              // GEMM-M grid == input grid
@@ -74,6 +76,7 @@ struct alignas(64) ConvProblem {
   sp_t* pool_lo;
   int pool_C;
   int group;              // generic kernel: number of consecutive problems launched as grid.z
+  int pair;               // 1: run on the CTA-pair (cta_group::2) persistent kernel (film_conv3x3_tc2.cu)
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)
@@ -85,5 +88,9 @@ void conv3x3_tc_plan(ConvProblem& h_prob, int num_sms);
 void conv3x3_tc_pick_tile(int H, int W, int B, int cout, int num_sms, int& tile_h, int& tile_w);
 cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
 cudaError_t conv3x3_tc_configure();
+// CTA-pair (cta_group::2, M = 256) variant: two vertically adjacent 16x8 tiles per work item
+bool conv3x3_tc2_plan(ConvProblem& h_prob, int num_sms);  // false if the problem is not eligible
+cudaError_t launch_conv3x3_tc2(const ConvProblem* d_prob, const ConvProblem& h_prob, cudaStream_t st);
+cudaError_t conv3x3_tc2_configure();
 
 }  // namespace film

@@ -1,0 +1,373 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the persistent 3x3 convolution (sm_100a).
+//
+// Two CTAs of a (2,1,1) cluster -- the two SMs of a TPC -- share every MMA: M = 256 output pixels
+// (two vertically adjacent 16x8 tiles, one per CTA), N = BN.  Each CTA TMA-loads ITS OWN
+// activation boxes and only HALF of the rows of every weight tap, so the weight bytes pulled from
+// L2 per MAC halve (the N <= 128 layers are L2-bandwidth bound on re-streamed weights), and one
+// instruction covers twice the work (the M=128 SS-mode instruction floor is ~72 cycles whatever N is).
+//
+// Protocol (CUTLASS PipelineTmaUmmaAsync 2-SM pattern):
+//   * "full" barriers live in the LEADER (cluster rank 0): the leader arms expect_tx for the bytes of
+//     BOTH CTAs; both producers issue cp.async.bulk.tensor...cta_group::2 whose complete_tx goes to
+//     the leader's barrier.
+//   * The leader's MMA warp issues tcgen05.mma.cta_group::2 and releases stages with
+//     tcgen05.commit...multicast::cluster (mask 0b11): the same "empty" barrier offset in both CTAs.
+//   * Accumulators: each CTA's TMEM holds its 128 rows; double-buffered.  t_full is multicast by the
+//     leader; t_empty lives in the leader and collects the epilogue warps of both CTAs (the peer
+//     arrives remotely through its shared::cluster address).
+//   * 3-pass split product, unfused (3 instructions per k-step, N = BN each): with half of B per CTA
+//     the [W_hi ; W_lo] concatenation trick of the single-CTA kernel does not apply.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "film_conv.h"
+#include "film_tc_ptx.cuh"
+
+namespace film {
+namespace {
+using namespace tc;
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kMaxRing = 8;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
+constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
+
+__host__ __device__ constexpr int a_stage_bytes2(int kc) { return 2 * (kTileH + 2) * kTileW * kc * 2; }
+__host__ __device__ constexpr int w_half_tap_bytes(int bn, int kc) { return (bn / 2) * kc * 2 * 2; }  // hi + lo halves
+
+template <int BN, int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    k_conv3x3_tc2(const ConvProblem* __restrict__ prob) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int kAPlane = (kTileH + 2) * kTileW * KC * 2;
+  constexpr int kAStage = 2 * kAPlane;
+  constexpr int kWHalf = (BN / 2) * KC * 2;   // one plane, half of the rows
+  constexpr int kWTap = 2 * kWHalf;           // hi half + lo half
+  constexpr int kRowStep = kTileW * KC * 2;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int NA = prob->v2_na, NW = prob->v2_nw;
+  const bool resident = prob->v2_resident != 0;
+  const int nsrc = prob->nsrc;
+  const int tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
+  const int pairs_y = (tiles_y + 1) / 2;
+  const int pairs_per_img = pairs_y * tiles_x;
+  const int cout = prob->cout;
+  const int n_nt = (cout + BN - 1) / BN;
+  const int nitems = prob->B * pairs_per_img * n_nt;   // work items: (tile pair, N tile), N fastest
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+  int nkb = 0;
+  for (int s = 0; s < nsrc; ++s) nkb += prob->src[s].nchunk * 9;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t w_base = a_base + (uint32_t)NA * kAStage;
+  const uint32_t w_bytes = resident ? (uint32_t)nkb * kWTap : (uint32_t)NW * kWTap;
+  const uint32_t tail = w_base + w_bytes;
+  const uint32_t tail_off = (uint32_t)NA * kAStage + w_bytes;
+  // barrier k at tail + 8k: a_full[0..7], a_empty[8..15], w_full[16..23], w_empty[24..31], t_full[32,33], t_empty[34,35]
+  auto a_full = [&](int s) { return tail + 8u * s; };
+  auto a_empty = [&](int s) { return tail + 8u * (kMaxRing + s); };
+  auto w_full = [&](int s) { return tail + 8u * (2 * kMaxRing + s); };
+  auto w_empty = [&](int s) { return tail + 8u * (3 * kMaxRing + s); };
+  auto t_full = [&](int s) { return tail + 8u * (4 * kMaxRing + s); };
+  auto t_empty = [&](int s) { return tail + 8u * (4 * kMaxRing + 2 + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_base + tail_off + kBarBytes);
+  float* bias_smem = reinterpret_cast<float*>(gen_base + tail_off + kBarBytes + 16);
+  int* src_tab = reinterpret_cast<int*>(gen_base + tail_off + kBarBytes + 16 + 512 * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 2 * kEpiWarps);  // epilogue warps of BOTH CTAs (leader's copy is the one used)
+    }
+    for (int s = 0; s < kMaxSrc; ++s) {
+      src_tab[2 * s] = s < nsrc ? prob->src[s].nchunk : 0;
+      src_tab[2 * s + 1] = s < nsrc ? prob->src[s].c_off : 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), kTmemCols);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < n_nt * BN; i += 32 * kEpiWarps) bias_smem[i] = (i < cout) ? prob->bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    const CUtensorMap* tm_w_hi = &prob->tm_w_hi_half;
+    const CUtensorMap* tm_w_lo = &prob->tm_w_lo_half;
+    const int n_half = (int)rank * (BN / 2);
+    if (resident) {
+      if (elect_one()) {
+        const uint32_t bar = map_to_cta(w_full(0), 0);
+        if (leader) mbar_expect_tx(w_full(0), 2u * (uint32_t)nkb * kWTap);   // both CTAs' halves
+        for (int kb = 0; kb < nkb; ++kb) {
+          tma_load_2d_2sm(w_base + kb * kWTap, tm_w_hi, bar, kb * KC, n_half);
+          tma_load_2d_2sm(w_base + kb * kWTap + kWHalf, tm_w_lo, bar, kb * KC, n_half);
+        }
+      }
+      __syncwarp();
+    }
+    uint32_t ia = 0, iw = 0;
+    for (int item = item0; item < nitems; item += item_step) {
+      const int sp = item / n_nt, n0 = (item % n_nt) * BN;
+      const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
+      const int y0 = (2 * (rem / tiles_x) + (int)rank) * kTileH, x0 = (rem % tiles_x) * kTileW;
+      int kb = 0;
+      for (int s = 0; s < nsrc; ++s) {
+        const int nchunk = src_tab[2 * s], c_off = src_tab[2 * s + 1];
+        const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
+        const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
+        for (int ch = 0; ch < nchunk; ++ch) {
+          for (int dx = 0; dx < 3; ++dx) {
+            const int st = ia % NA;
+            mbar_wait(a_empty(st), ((ia / NA) & 1u) ^ 1u);
+            if (elect_one()) {
+              const uint32_t sa = a_base + st * kAStage;
+              const uint32_t bar = map_to_cta(a_full(st), 0);
+              if (leader) mbar_expect_tx(a_full(st), 2u * kAStage);
+              tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+            }
+            __syncwarp();
+            ++ia;
+            if (!resident) {
+              for (int dy = 0; dy < 3; ++dy, ++kb) {
+                const int ws = iw % NW;
+                mbar_wait(w_empty(ws), ((iw / NW) & 1u) ^ 1u);
+                if (elect_one()) {
+                  const uint32_t sw = w_base + ws * kWTap;
+                  const uint32_t bar = map_to_cta(w_full(ws), 0);
+                  if (leader) mbar_expect_tx(w_full(ws), 2u * kWTap);
+                  tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n0 + n_half);
+                  tma_load_2d_2sm(sw + kWHalf, tm_w_lo, bar, kb * KC, n0 + n_half);
+                }
+                __syncwarp();
+                ++iw;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    if (leader) {
+      const uint32_t idesc = make_idesc_m<BN, 256>();
+      if (resident) {
+        mbar_wait(w_full(0), 0);
+        tc_fence_after();
+      }
+      const int nab = nkb / 3;
+      uint32_t ia = 0, iw = 0, it = 0;
+      for (int item = item0; item < nitems; item += item_step, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        int kb = 0;
+        for (int ab = 0; ab < nab; ++ab) {
+          const int st = ia % NA;
+          mbar_wait(a_full(st), (ia / NA) & 1u);
+          tc_fence_after();
+          const uint32_t sa = a_base + st * kAStage;
+          for (int dy = 0; dy < 3; ++dy, ++kb) {
+            uint32_t sw;
+            int ws = 0;
+            if (resident) {
+              sw = w_base + kb * kWTap;
+            } else {
+              ws = iw % NW;
+              mbar_wait(w_full(ws), (iw / NW) & 1u);
+              tc_fence_after();
+              sw = w_base + ws * kWTap;
+            }
+            if (elect_one()) {
+              const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
+              const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
+              const uint32_t first = (kb == 0) ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                umma_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
+                umma_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              }
+              if (!resident) umma_commit_2sm_mc(w_empty(ws));
+              if (dy == 2) umma_commit_2sm_mc(a_empty(st));
+              if (dy == 2 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+            }
+            __syncwarp();
+            if (!resident) ++iw;
+          }
+          ++ia;
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue (warps 2..9, both CTAs) ============================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int H = prob->H, W = prob->W, out_H = prob->out_H, out_W = prob->out_W, out_C = prob->out_C;
+    const int out_c_off = prob->out_c_off, act = prob->act;
+    sp_t* const out_hi = prob->out_hi;
+    sp_t* const out_lo = prob->out_lo;
+    sp_t* const pool_hi = prob->pool_hi;
+    sp_t* const pool_lo = prob->pool_lo;
+    const int pool_C = prob->pool_C;
+    const bool do_pool = pool_hi != nullptr;
+    const uint32_t t_empty_leader0 = map_to_cta(t_empty(0), 0), t_empty_leader1 = map_to_cta(t_empty(1), 0);
+    uint32_t it = 0;
+    for (int item = item0; item < nitems; item += item_step, ++it) {
+      const uint32_t acc = it & 1u;
+      const int sp = item / n_nt, n0 = (item % n_nt) * BN;
+      const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
+      const int py = (2 * (rem / tiles_x) + (int)rank) * kTileH + r / kTileW, px = (rem % tiles_x) * kTileW + r % kTileW;
+      const bool valid = (py < H) && (px < W);
+      const int64_t opix = ((int64_t)b * out_H + py) * out_W + px;
+      sp_t* oh = out_hi + opix * out_C + out_c_off + n0;
+      sp_t* ol = out_lo + opix * out_C + out_c_off + n0;
+      mbar_wait(t_full(acc), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = half; cc < BN / 16; cc += 2) {
+        if (n0 + cc * 16 >= cout) break;
+        uint32_t v[16];
+        tmem_ld16(t_addr + (uint32_t)(cc * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 16 + g * 8 + j];
+            f[j] = act ? leaky(x) : x;
+          }
+          if (valid) {
+            uint4 h, l;
+            pack8(f, h, l);
+            *reinterpret_cast<uint4*>(oh + cc * 16 + g * 8) = h;
+            *reinterpret_cast<uint4*>(ol + cc * 16 + g * 8) = l;
+          }
+          if (do_pool) {
+            float pf[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
+              pf[j] = (a + __shfl_xor_sync(0xffffffffu, a, 8)) * 0.25f;
+            }
+            if (valid && !(lane & 1) && !(lane & 8)) {
+              const int64_t ppix = ((int64_t)b * (out_H >> 1) + (py >> 1)) * (out_W >> 1) + (px >> 1);
+              uint4 h, l;
+              pack8(pf, h, l);
+              *reinterpret_cast<uint4*>(pool_hi + ppix * pool_C + n0 + cc * 16 + g * 8) = h;
+              *reinterpret_cast<uint4*>(pool_lo + ppix * pool_C + n0 + cc * 16 + g * 8) = l;
+            }
+          }
+        }
+      }
+      // this CTA's half of the accumulator is drained: tell the leader's MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? t_empty_leader1 : t_empty_leader0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while the peer can still signal / read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+int smem_bytes_for2(const ConvProblem& h, int bn) {
+  const int nkb = h.ktot / h.kchunk;
+  const int w = h.v2_resident ? nkb * w_half_tap_bytes(bn, h.kchunk) : h.v2_nw * w_half_tap_bytes(bn, h.kchunk);
+  return h.v2_na * a_stage_bytes2(h.kchunk) + w + kFixedBytes;
+}
+
+}  // namespace
+
+int conv_tc_block_n(int cout);
+
+bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
+  const int bn = conv_tc_block_n(h.cout);
+  if (h.ntaps != 9 || h.tile_h != kTileH || h.tile_w != kTileW) return false;
+  if (h.kchunk == 32 && bn != 32) return false;
+  if (h.cout % bn) return false;            // whole N tiles only (the half-row boxes must not straddle Cout)
+  const int nkb = h.ktot / h.kchunk;
+  const int wtap = w_half_tap_bytes(bn, h.kchunk);
+  const int w_all = nkb * wtap;
+  const int a_stage = a_stage_bytes2(h.kchunk);
+  h.v2_resident = 0;
+  if (h.cout <= bn && 2 * (long)nkb * wtap < (1 << 20) && w_all + 2 * a_stage + kFixedBytes <= kSmemLimit) {
+    h.v2_resident = 1;
+    int na = (kSmemLimit - kFixedBytes - w_all) / a_stage;
+    h.v2_na = na > 6 ? 6 : na;
+    h.v2_nw = 1;
+  } else {
+    h.v2_na = 3;
+    int nw = (kSmemLimit - kFixedBytes - h.v2_na * a_stage) / wtap;
+    h.v2_nw = nw > kMaxRing ? kMaxRing : nw;
+    if (h.v2_nw < 2) return false;
+  }
+  const int pairs_y = (h.tiles_y + 1) / 2;
+  const int nitems = h.B * pairs_y * h.tiles_x * ((h.cout + bn - 1) / bn);
+  int grid = 2 * nitems;
+  const int max_grid = num_sms & ~1;
+  h.v2_grid = grid < max_grid ? grid : max_grid;
+  h.pair = 1;
+  return true;
+}
+
+cudaError_t conv3x3_tc2_configure() {
+  cudaError_t e;
+#define FILM_CFG(BN, KC)                                                                                      \
+  e = cudaFuncSetAttribute(k_conv3x3_tc2<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);   \
+  if (e != cudaSuccess) return e;
+  FILM_CFG(32, 64) FILM_CFG(64, 64) FILM_CFG(128, 64) FILM_CFG(256, 64) FILM_CFG(32, 32)
+#undef FILM_CFG
+  return cudaSuccess;
+}
+
+cudaError_t launch_conv3x3_tc2(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
+  const int bn = conv_tc_block_n(h.cout);
+  const int smem = smem_bytes_for2(h, bn);
+  if (h.kchunk == 32) {
+    k_conv3x3_tc2<32, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);
+    return cudaGetLastError();
+  }
+  switch (bn) {
+    case 256: k_conv3x3_tc2<256, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    case 128: k_conv3x3_tc2<128, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    case 64: k_conv3x3_tc2<64, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+    default: k_conv3x3_tc2<32, 64><<<h.v2_grid, kThreads, smem, st>>>(d_prob); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace film

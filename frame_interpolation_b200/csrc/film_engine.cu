@@ -417,7 +417,7 @@ struct DebugTensor {
 struct Plan {
   int h, w, H, W, off_y, off_x;
   int conv_impl;
-  int conv3x3_v2 = 1, num_sms = 148;
+  int conv3x3_v2 = 1, num_sms = 148, conv3x3_2cta = 0;
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -514,8 +514,12 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1 &&
                   (kc == kChunk || pc.cout <= 32);
   int box_h, box_w;
+  // CTA-pair kernel: large levels only (it needs 16x8 tiles and enough tile pairs to fill the SM pairs)
+  const bool want_pair = v2 && P.conv3x3_2cta &&
+                         (P.conv3x3_2cta >= 2 ||  // >= 2: every eligible layer (testing)
+                          (long)cp.B * ((cp.H + 15) / 16) * ((cp.W + 7) / 8) >= 4L * P.num_sms);
   if (v2) {
-    if (pool_out) {
+    if (pool_out || want_pair) {
       cp.tile_h = 16;  // the fused pool maps 2x2 partners to lanes l^1 / l^8 of a 16x8 tile
       cp.tile_w = 8;
     } else {
@@ -556,6 +560,8 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   const int bn = conv_tc_block_n(pc.cout);
   make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn, kc);
   make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn, kc);
+  make_w_map(&cp.tm_w_hi_half, pc.w_hi, pc.cout, pc.ktot, bn / 2, kc);
+  make_w_map(&cp.tm_w_lo_half, pc.w_lo, pc.cout, pc.ktot, bn / 2, kc);
   if (out) {
     cp.out_hi = out->hi;
     cp.out_lo = out->lo;
@@ -580,7 +586,10 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     cp.pool_C = pool_out->C;
   }
   cp.group = 1;
-  if (v2) conv3x3_tc_plan(cp, P.num_sms);
+  cp.pair = 0;
+  bool pair = false;
+  if (want_pair) pair = conv3x3_tc2_plan(cp, P.num_sms);
+  if (v2 && !pair) conv3x3_tc_plan(cp, P.num_sms);
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
@@ -589,8 +598,9 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   if (no_op) return idx;  // the caller launches this problem as part of a group
   Plan* pp = &P;
   const int impl = P.conv_impl;
-  P.add_op(0, tag, [pp, idx, impl, v2](cudaStream_t st) {
+  P.add_op(0, tag, [pp, idx, impl, v2, pair](cudaStream_t st) {
     if (impl == 1) return launch_conv_simt(pp->d_probs + idx, pp->h_probs[idx], st);
+    if (pair) return launch_conv3x3_tc2(pp->d_probs + idx, pp->h_probs[idx], st);
     return v2 ? launch_conv3x3_tc(pp->d_probs + idx, pp->h_probs[idx], st)
               : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
   }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W);
@@ -598,13 +608,14 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
 }
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
-                                        int conv3x3_v2, int num_sms) {
+                                        int conv3x3_v2, int num_sms, int conv3x3_2cta) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
   P.h = h;
   P.w = w;
   P.conv_impl = conv_impl;
   P.conv3x3_v2 = conv3x3_v2;
+  P.conv3x3_2cta = conv3x3_2cta;
   P.num_sms = num_sms;
   // eval/interpolator.py:30-63
   int ph = 0, pw = 0;
@@ -931,6 +942,7 @@ struct film_handle {
   cudaEvent_t fork_event = nullptr;
   int use_lanes = 0;   // stream lanes measured no gain at 1080p (smem-saturating kernels cannot co-reside)
   int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
+  int conv3x3_2cta = 0;  // CTA-pair (cta_group::2) variant on the large levels
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
@@ -977,12 +989,12 @@ static void enqueue_plan(film_handle* h, Plan* P, cudaStream_t origin) {
 
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
-  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes);
+  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
+           h->use_lanes, h->conv3x3_2cta);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2,
-                                       h->num_sms);
+                                       h->num_sms, h->conv3x3_2cta);
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1062,6 +1074,8 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     for (auto& e : h->ev) FILM_CUDA(cudaEventCreate(&e));
     FILM_CUDA(conv_tc_configure());
     FILM_CUDA(conv3x3_tc_configure());
+    FILM_CUDA(conv3x3_tc2_configure());
+    if (const char* e2 = getenv("FILM_2CTA")) h->conv3x3_2cta = atoi(e2);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
     h->model.reset(new Model);
@@ -1103,6 +1117,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "time_ops") h->time_ops = value;
   else if (n == "use_lanes") h->use_lanes = value;
   else if (n == "conv3x3_v2") h->conv3x3_v2 = value;
+  else if (n == "conv3x3_2cta") h->conv3x3_2cta = value;
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;
