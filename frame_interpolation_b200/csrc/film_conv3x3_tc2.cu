@@ -15,8 +15,12 @@
 //   * Accumulators: each CTA's TMEM holds its 128 rows; double-buffered.  t_full is multicast by the
 //     leader; t_empty lives in the leader and collects the epilogue warps of both CTAs (the peer
 //     arrives remotely through its shared::cluster address).
-//   * 3-pass split product, unfused (3 instructions per k-step, N = BN each): with half of B per CTA
-//     the [W_hi ; W_lo] concatenation trick of the single-CTA kernel does not apply.
+//   * 3-pass split product.  BN >= 128: unfused, 3 instructions per k-step (N = BN), each CTA loads
+//     half of the W_hi rows and half of the W_lo rows (weight bytes per CTA x0.5).
+//     BN <= 64 (instruction-bound): fused, 2 instructions per k-step.  The B operand of a
+//     cta_group::2 MMA is split by rows across the pair, so for  A_hi x [W_hi ; W_lo]  (N = 2*BN) the
+//     leader holds ALL of W_hi and the peer ALL of W_lo at the same smem offset; for  A_lo x W_hi
+//     (N = BN) each CTA additionally holds its half of W_hi (weight bytes per CTA x0.75).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,7 +41,12 @@ constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
 
 __host__ __device__ constexpr int a_stage_bytes2(int kc) { return 2 * (kTileH + 2) * kTileW * kc * 2; }
-__host__ __device__ constexpr int w_half_tap_bytes(int bn, int kc) { return (bn / 2) * kc * 2 * 2; }  // hi + lo halves
+// bytes of one weight tap per CTA: unfused = half of W_hi + half of W_lo; fused (BN <= 64) = one full
+// plane (W_hi in the leader, W_lo in the peer) + this CTA's half of W_hi
+__host__ __device__ constexpr bool pair_fused(int bn) { return bn <= 64; }
+__host__ __device__ constexpr int w_half_tap_bytes(int bn, int kc) {
+  return pair_fused(bn) ? (bn + bn / 2) * kc * 2 : (bn / 2) * kc * 2 * 2;
+}
 
 template <int BN, int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -45,10 +54,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   constexpr int kAPlane = (kTileH + 2) * kTileW * KC * 2;
   constexpr int kAStage = 2 * kAPlane;
+  constexpr bool kFused = pair_fused(BN);
   constexpr int kWHalf = (BN / 2) * KC * 2;   // one plane, half of the rows
-  constexpr int kWTap = 2 * kWHalf;           // hi half + lo half
+  constexpr int kWFull = BN * KC * 2;         // one plane, all rows of the N tile
+  constexpr int kWTap = w_half_tap_bytes(BN, KC);
   constexpr int kRowStep = kTileW * KC * 2;
-  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
+  constexpr uint32_t kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -117,14 +129,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // ============================ TMA producer (both CTAs) ============================
     const CUtensorMap* tm_w_hi = &prob->tm_w_hi_half;
     const CUtensorMap* tm_w_lo = &prob->tm_w_lo_half;
+    const CUtensorMap* tm_w_full_hi = &prob->tm_w_hi;   // fused form: full-height boxes [BN x KC]
+    const CUtensorMap* tm_w_full_lo = &prob->tm_w_lo;
     const int n_half = (int)rank * (BN / 2);
     if (resident) {
       if (elect_one()) {
         const uint32_t bar = map_to_cta(w_full(0), 0);
         if (leader) mbar_expect_tx(w_full(0), 2u * (uint32_t)nkb * kWTap);   // both CTAs' halves
         for (int kb = 0; kb < nkb; ++kb) {
-          tma_load_2d_2sm(w_base + kb * kWTap, tm_w_hi, bar, kb * KC, n_half);
-          tma_load_2d_2sm(w_base + kb * kWTap + kWHalf, tm_w_lo, bar, kb * KC, n_half);
+          if constexpr (kFused) {
+            tma_load_2d_2sm(w_base + kb * kWTap, leader ? tm_w_full_hi : tm_w_full_lo, bar, kb * KC, 0);
+            tma_load_2d_2sm(w_base + kb * kWTap + kWFull, tm_w_hi, bar, kb * KC, n_half);
+          } else {
+            tma_load_2d_2sm(w_base + kb * kWTap, tm_w_hi, bar, kb * KC, n_half);
+            tma_load_2d_2sm(w_base + kb * kWTap + kWHalf, tm_w_lo, bar, kb * KC, n_half);
+          }
         }
       }
       __syncwarp();
@@ -160,8 +179,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   const uint32_t sw = w_base + ws * kWTap;
                   const uint32_t bar = map_to_cta(w_full(ws), 0);
                   if (leader) mbar_expect_tx(w_full(ws), 2u * kWTap);
-                  tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n0 + n_half);
-                  tma_load_2d_2sm(sw + kWHalf, tm_w_lo, bar, kb * KC, n0 + n_half);
+                  if constexpr (kFused) {
+                    tma_load_2d_2sm(sw, leader ? tm_w_full_hi : tm_w_full_lo, bar, kb * KC, n0);
+                    tma_load_2d_2sm(sw + kWFull, tm_w_hi, bar, kb * KC, n0 + n_half);
+                  } else {
+                    tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n0 + n_half);
+                    tma_load_2d_2sm(sw + kWHalf, tm_w_lo, bar, kb * KC, n0 + n_half);
+                  }
                 }
                 __syncwarp();
                 ++iw;
@@ -175,6 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // ============================ MMA issuer (leader CTA only) ============================
     if (leader) {
       const uint32_t idesc = make_idesc_m<BN, 256>();
+      const uint32_t idesc2 = make_idesc_m<(kFused ? 2 * BN : BN), 256>();
       if (resident) {
         mbar_wait(w_full(0), 0);
         tc_fence_after();
@@ -185,7 +210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t acc = it & 1u;
         mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
         int kb = 0;
         for (int ab = 0; ab < nab; ++ab) {
           const int st = ia % NA;
@@ -205,14 +230,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
             if (elect_one()) {
               const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
-              const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
               const uint32_t first = (kb == 0) ? 0u : 1u;
+              if constexpr (kFused) {
+                // region X (leader: W_hi, peer: W_lo) is the 2*BN-row operand; region Y = halves of W_hi
+                const uint64_t w_x = make_desc_kc<KC>(sw), w_y = make_desc_kc<KC>(sw + kWFull);
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                umma_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
-                umma_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-                umma_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+                for (int k = 0; k < KC / 16; ++k) {
+                  const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                  umma_2sm(d_tmem, a_hi + adv, w_x + adv, idesc2, k == 0 ? first : 1u);
+                  umma_2sm(d_tmem, a_lo + adv, w_y + adv, idesc, 1u);
+                }
+              } else {
+                const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                  umma_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
+                  umma_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                  umma_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+                }
               }
               if (!resident) umma_commit_2sm_mc(w_empty(ws));
               if (dy == 2) umma_commit_2sm_mc(a_empty(st));
@@ -251,13 +287,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       sp_t* ol = out_lo + opix * out_C + out_c_off + n0;
       mbar_wait(t_full(acc), (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = half; cc < BN / 16; cc += 2) {
         if (n0 + cc * 16 >= cout) break;
         uint32_t v[16];
         tmem_ld16(t_addr + (uint32_t)(cc * 16), v);
-        tmem_ld_wait();
+        if constexpr (kFused) {
+          uint32_t u[16];
+          tmem_ld16(t_addr + (uint32_t)(BN + cc * 16), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        } else {
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           float f[8];

@@ -588,8 +588,16 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.group = 1;
   cp.pair = 0;
   bool pair = false;
-  if (want_pair) pair = conv3x3_tc2_plan(cp, P.num_sms);
-  if (v2 && !pair) conv3x3_tc_plan(cp, P.num_sms);
+  if (v2) conv3x3_tc_plan(cp, P.num_sms);
+  // the pair kernel pays off where weights are re-streamed per tile (halved weight bytes per CTA);
+  // layers whose weights stay resident in one CTA's smem are faster on the single-CTA fused kernel
+  if (want_pair && (!cp.v2_resident || P.conv3x3_2cta >= 2)) {
+    ConvProblem alt = cp;
+    if (conv3x3_tc2_plan(alt, P.num_sms)) {
+      cp = alt;
+      pair = true;
+    }
+  }
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
