@@ -950,7 +950,7 @@ struct film_handle {
   cudaEvent_t fork_event = nullptr;
   int use_lanes = 0;   // stream lanes measured no gain at 1080p (smem-saturating kernels cannot co-reside)
   int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
-  int conv3x3_2cta = 0;  // CTA-pair (cta_group::2) variant on the large levels
+  int conv3x3_2cta = 1;  // CTA-pair (cta_group::2) kernel for streamed-weight 3x3 convs on the large levels
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;

@@ -120,6 +120,8 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read
  *   "time_ops"    : 1 = run eagerly with one CUDA-event pair per kernel (see film_op_table)
  *   "conv3x3_v2"  : 1 = persistent tap-reuse kernel for 3x3 convs (default), 0 = generic kernel
+ *   "conv3x3_2cta": 1 = CTA-pair (tcgen05 cta_group::2, M = 256) kernel for the streamed-weight 3x3
+ *                   convs of the large pyramid levels (default), 0 = off, 2 = every eligible layer
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0) */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
 

@@ -256,3 +256,19 @@ def test_cli_end_to_end(tmp_path, synthetic_weights):
                                    synthetic_weights[0], "--block_height", "2", "--block_width", "2",
                                    "--output_frame", str(tmp_path / "mid.png")]) == 0
     np.testing.assert_array_equal(mid, eval_util.read_image(str(tmp_path / "mid.png")))
+
+
+@pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0)])
+def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
+    """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers) meets the same bar."""
+    from frame_interpolation_b200.interpolator import Interpolator
+    x0, x1 = synthetic.frame_pair(256, 320, seed=13, n_waves=8)
+    ref = oracle(x0, x1, DT)
+    eng = Interpolator(synthetic_weights[0], align=64)
+    eng.set_option(option, value)
+    out = eng(x0, x1, DT)
+    assert np.abs(out.astype(np.float64) - ref).max() < TIGHT
+    default = Interpolator(synthetic_weights[0], align=64)
+    assert np.abs(out - default(x0, x1, DT)).max() < 1e-4
+    eng.close()
+    default.close()
