@@ -591,7 +591,9 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   if (v2) conv3x3_tc_plan(cp, P.num_sms);
   // the pair kernel pays off where weights are re-streamed per tile (halved weight bytes per CTA);
   // layers whose weights stay resident in one CTA's smem are faster on the single-CTA fused kernel
-  if (want_pair && (!cp.v2_resident || P.conv3x3_2cta >= 2)) {
+  // (measured at 1080p, profiles/r1k: resident 9-K-block layers lose ~15 % on the pair kernel, the
+  // 18-K-block 128->32 flow conv gains 28 %)
+  if (want_pair && (!cp.v2_resident || cp.ktot / cp.kchunk >= 18 || P.conv3x3_2cta >= 2)) {
     ConvProblem alt = cp;
     if (conv3x3_tc2_plan(alt, P.num_sms)) {
       cp = alt;
