@@ -947,6 +947,12 @@ struct film_handle {
   std::string err;
   int conv_impl = 0, use_graph = 1, keep_debug = 0, time_ops = 0;
   bool dev_events_valid = false;  // ev[1]/ev[2] bracket the last device-pointer call
+  cudaStream_t copy_stream = nullptr;   // H2D / D2H of tile t+1 / t-1 overlaps the network call of tile t
+  float* stage_in[2] = {nullptr, nullptr};
+  float* stage_out[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
   cudaStream_t lane_streams[Plan::kNumLanes] = {};  // lane 0 = the origin stream of the call
   std::vector<cudaEvent_t> token_events;
   cudaEvent_t fork_event = nullptr;
@@ -1109,6 +1115,13 @@ void film_destroy(film_handle* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->op_events) cudaEventDestroy(e);
   for (auto& e : h->token_events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_in[i]) cudaFree(h->stage_in[i]);
+    if (h->stage_out[i]) cudaFree(h->stage_out[i]);
+    for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_free[i], h->ev_out[i]})
+      if (e) cudaEventDestroy(e);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (int i = 1; i < Plan::kNumLanes; ++i)
     if (h->lane_streams[i]) cudaStreamDestroy(h->lane_streams[i]);
@@ -1146,6 +1159,73 @@ int film_synchronize(film_handle* h) {
   }
 }
 
+extern "C++" {
+// Double-buffered device staging for the multi-call paths (tiles, batches): [2 frames in] / [1 frame out]
+static void ensure_staging(film_handle* h, size_t frame_bytes) {
+  if (!h->copy_stream) FILM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    if (!h->ev_in[i]) {
+      FILM_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      FILM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+      FILM_CUDA(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+      FILM_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  if (h->stage_bytes >= frame_bytes) return;
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_in[i]) cudaFree(h->stage_in[i]);
+    if (h->stage_out[i]) cudaFree(h->stage_out[i]);
+    h->stage_in[i] = h->stage_out[i] = nullptr;
+  }
+  h->stage_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    FILM_CUDA(cudaMalloc(&h->stage_in[i], 2 * frame_bytes));
+    FILM_CUDA(cudaMalloc(&h->stage_out[i], frame_bytes));
+  }
+  h->stage_bytes = frame_bytes;
+}
+
+// Runs `n` independent network calls of plan P with copies overlapped: item i's inputs are fetched by
+// `fetch(i, dst_x0, dst_x1, stream)` (host -> device staging) and its result is delivered by
+// `deliver(i, src, stream)`; while item i computes on the handle's stream, item i+1 uploads and item
+// i-1 downloads on the copy stream.
+template <class Fetch, class Deliver>
+static void run_pipelined(film_handle* h, Plan* P, int n, size_t frame_bytes, Fetch fetch, Deliver deliver) {
+  ensure_staging(h, frame_bytes);
+  cudaStream_t cs = h->copy_stream, ms = h->stream;
+  FILM_CUDA(cudaStreamSynchronize(ms));
+  FILM_CUDA(cudaStreamSynchronize(cs));
+  for (int i = 0; i < n; ++i) {
+    const int b = i & 1;
+    // upload item i (its staging buffer was released by the compute of item i-2)
+    if (i >= 2) FILM_CUDA(cudaStreamWaitEvent(cs, h->ev_free[b], 0));
+    fetch(i, h->stage_in[b], (float*)((char*)h->stage_in[b] + frame_bytes), cs);
+    FILM_CUDA(cudaEventRecord(h->ev_in[b], cs));
+    // compute item i
+    FILM_CUDA(cudaStreamWaitEvent(ms, h->ev_in[b], 0));
+    FILM_CUDA(cudaMemcpyAsync(P->xin, h->stage_in[b], 2 * frame_bytes, cudaMemcpyDeviceToDevice, ms));
+    FILM_CUDA(cudaEventRecord(h->ev_free[b], ms));
+    run_plan(h, P, ms);
+    if (i >= 2) FILM_CUDA(cudaStreamWaitEvent(ms, h->ev_out[b], 0));  // stage_out[b] drained by item i-2's download
+    FILM_CUDA(cudaMemcpyAsync(h->stage_out[b], P->xout, frame_bytes, cudaMemcpyDeviceToDevice, ms));
+    FILM_CUDA(cudaEventRecord(h->ev_done[b], ms));
+    // download item i-1 (overlaps the compute of item i, already enqueued)
+    if (i >= 1) {
+      const int pb = (i - 1) & 1;
+      FILM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[pb], 0));
+      deliver(i - 1, h->stage_out[pb], cs);
+      FILM_CUDA(cudaEventRecord(h->ev_out[pb], cs));
+    }
+  }
+  const int lb = (n - 1) & 1;
+  FILM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[lb], 0));
+  deliver(n - 1, h->stage_out[lb], cs);
+  FILM_CUDA(cudaStreamSynchronize(cs));
+  FILM_CUDA(cudaStreamSynchronize(ms));
+}
+
+}  // extern "C++"
+
 static void check_frame_args(const void* x0, const void* x1, const void* out, int B, int H, int W) {
   if (!x0 || !x1 || !out) throw Error{FILM_ERR_ARG, "null frame pointer"};
   if (B < 1 || H < 1 || W < 1) throw Error{FILM_ERR_ARG, "batch, height and width must be positive"};
@@ -1177,6 +1257,19 @@ int film_interpolate(film_handle* h, const float* x0, const float* x1, const flo
     Plan* P = get_plan(h, H, W, align);
     const size_t frame = (size_t)H * W * 3 * sizeof(float);
     float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
+    if (B > 1 && !h->time_ops) {
+      // batch of pairs: uploads / downloads of neighbouring pairs overlap the network calls
+      run_pipelined(h, P, B, frame,
+                    [&](int b, float* d0, float* d1, cudaStream_t cs) {
+                      FILM_CUDA(cudaMemcpyAsync(d0, (const char*)x0 + b * frame, frame, cudaMemcpyHostToDevice, cs));
+                      FILM_CUDA(cudaMemcpyAsync(d1, (const char*)x1 + b * frame, frame, cudaMemcpyHostToDevice, cs));
+                    },
+                    [&](int b, const float* src, cudaStream_t cs) {
+                      FILM_CUDA(cudaMemcpyAsync((char*)out + b * frame, src, frame, cudaMemcpyDeviceToHost, cs));
+                    });
+      fill_profile(h, P, 0.f, 0.f, 0.f);
+      return FILM_OK;
+    }
     for (int b = 0; b < B; ++b) {
       FILM_CUDA(cudaEventRecord(h->ev[0], h->stream));
       FILM_CUDA(cudaMemcpyAsync(P->xin, (const char*)x0 + b * frame, frame, cudaMemcpyHostToDevice, h->stream));
@@ -1248,6 +1341,22 @@ int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, con
     Plan* P = get_plan(h, ph, pw, align);
     const size_t row = (size_t)pw * 3 * sizeof(float), full_row = (size_t)W * 3 * sizeof(float);
     float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
+    if (block_h * block_w > 1 && !h->time_ops) {
+      // tiles in row-major order (eval/interpolator.py:199-202), each padded on its own; the strided
+      // upload of tile t+1 and download of tile t-1 overlap the network call of tile t
+      const size_t tile_bytes = (size_t)ph * pw * 3 * sizeof(float);
+      auto tile_off = [&](int t) { return ((size_t)(t / block_w) * ph * W + (size_t)(t % block_w) * pw) * 3; };
+      run_pipelined(h, P, block_h * block_w, tile_bytes,
+                    [&](int t, float* d0, float* d1, cudaStream_t cs) {
+                      FILM_CUDA(cudaMemcpy2DAsync(d0, row, x0 + tile_off(t), full_row, row, ph, cudaMemcpyHostToDevice, cs));
+                      FILM_CUDA(cudaMemcpy2DAsync(d1, row, x1 + tile_off(t), full_row, row, ph, cudaMemcpyHostToDevice, cs));
+                    },
+                    [&](int t, const float* src, cudaStream_t cs) {
+                      FILM_CUDA(cudaMemcpy2DAsync(out + tile_off(t), full_row, src, row, row, ph, cudaMemcpyDeviceToHost, cs));
+                    });
+      fill_profile(h, P, 0.f, 0.f, 0.f);
+      return FILM_OK;
+    }
     // tiles are processed in row-major order (eval/interpolator.py:199-202), each padded on its own
     for (int r = 0; r < block_h; ++r)
       for (int c = 0; c < block_w; ++c) {
@@ -1287,6 +1396,8 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
     Plan* P = get_plan(h, H, W, align);
     const int n = (1 << times_to_interpolate) + 1;
     const size_t frame = (size_t)H * W * 3 * sizeof(float);
+    ensure_staging(h, 16);  // creates the copy stream
+    std::vector<std::pair<int, cudaEvent_t>> frame_events;
     float* seq = nullptr;
     FILM_CUDA(cudaMalloc(&seq, frame * n));
     cudaError_t e = cudaSuccess;
@@ -1310,12 +1421,27 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
           }
         }
         chk(cudaMemcpyAsync(slot(i), P->xout, frame, cudaMemcpyDeviceToDevice, h->stream));
+        if (e == cudaSuccess) {
+          cudaEvent_t ev;
+          chk(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          chk(cudaEventRecord(ev, h->stream));
+          frame_events.push_back({i, ev});
+        }
       }
     }
     chk(cudaEventRecord(h->ev[2], h->stream));
-    chk(cudaMemcpyAsync(out, seq, frame * n, cudaMemcpyDeviceToHost, h->stream));
+    // everything is enqueued; download each mid-frame as soon as it exists (copy stream), while the
+    // deeper recursion levels are still computing
+    memcpy(out, frame0, frame);
+    memcpy((char*)out + frame * (n - 1), frame1, frame);
+    for (auto& fe : frame_events) {
+      chk(cudaStreamWaitEvent(h->copy_stream, fe.second, 0));
+      chk(cudaMemcpyAsync((char*)out + frame * fe.first, slot(fe.first), frame, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    chk(cudaStreamSynchronize(h->copy_stream));
     chk(cudaEventRecord(h->ev[3], h->stream));
     chk(cudaStreamSynchronize(h->stream));
+    for (auto& fe : frame_events) cudaEventDestroy(fe.second);
     float t_h2d = 0, t_net = 0, t_d2h = 0;
     if (e == cudaSuccess) {
       cudaEventElapsedTime(&t_h2d, h->ev[0], h->ev[1]);
