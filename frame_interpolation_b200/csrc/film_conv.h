@@ -77,6 +77,8 @@ struct alignas(64) ConvProblem {
   int pool_C;
   int group;              // generic kernel: number of consecutive problems launched as grid.z
   int pair;               // 1: run on the CTA-pair (cta_group::2) persistent kernel (film_conv3x3_tc2.cu)
+  int bn;                 // N tile (32/64/128/256): conv_tc_block_n(cout), or smaller on tiny levels so that
+                          // a K-serial problem spreads over more SMs
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)

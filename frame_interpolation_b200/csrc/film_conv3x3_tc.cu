@@ -357,7 +357,7 @@ void conv3x3_tc_pick_tile(int H, int W, int B, int cout, int num_sms, int& tile_
 
 // Chooses resident/streamed weights and the ring depths for one 3x3 problem.
 void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
-  const int bn = conv_tc_block_n(h.cout);
+  const int bn = h.bn;
   const int nkb = h.ktot / h.kchunk;
   const int wtap = w_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
@@ -388,7 +388,7 @@ cudaError_t conv3x3_tc_configure() {
 }
 
 cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
-  const int bn = conv_tc_block_n(h.cout);
+  const int bn = h.bn;
   const int smem = smem_bytes_for(h, bn);
   if (h.kchunk == 32) {
     if (bn != 32) return cudaErrorInvalidValue;  // only the 32 -> 32 flow convs use 32-channel K blocks

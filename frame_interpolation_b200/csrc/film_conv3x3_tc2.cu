@@ -359,7 +359,7 @@ int smem_bytes_for2(const ConvProblem& h, int bn) {
 int conv_tc_block_n(int cout);
 
 bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
-  const int bn = conv_tc_block_n(h.cout);
+  const int bn = h.bn;
   if (h.ntaps != 9 || h.tile_h != kTileH || h.tile_w != kTileW) return false;
   if (h.kchunk == 32 && bn != 32) return false;
   if (h.cout % bn) return false;            // whole N tiles only (the half-row boxes must not straddle Cout)
@@ -399,7 +399,7 @@ cudaError_t conv3x3_tc2_configure() {
 }
 
 cudaError_t launch_conv3x3_tc2(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
-  const int bn = conv_tc_block_n(h.cout);
+  const int bn = h.bn;
   const int smem = smem_bytes_for2(h, bn);
   if (h.kchunk == 32) {
     k_conv3x3_tc2<32, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);

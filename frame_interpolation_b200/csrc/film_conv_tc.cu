@@ -288,7 +288,7 @@ cudaError_t conv_tc_configure() {
 }
 
 cudaError_t launch_conv_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
-  const int bn = conv_tc_block_n(h.cout);
+  const int bn = h.bn;
   if (h.kchunk == 32) {
     if (bn == 64) return launch_bn<64, 32>(d_prob, h, st);
     if (bn == 32) return launch_bn<32, 32>(d_prob, h, st);

@@ -557,7 +557,14 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.bias = pc.bias;
   cp.cout = pc.cout;
   cp.act = act;
-  const int bn = conv_tc_block_n(pc.cout);
+  int bn = conv_tc_block_n(pc.cout);
+  if (out && !pool_out) {
+    // tiny pyramid levels: a 17x30 level has 8 tiles but K = 17280 -- split N into smaller tiles so the
+    // K-serial work spreads over more SMs (and BN <= 128 tiles use the 2-instruction product)
+    auto items = [&](int b) { return (long)cp.B * cp.tiles_y * cp.tiles_x * ((pc.cout + b - 1) / b); };
+    while (bn > 64 && items(bn) < P.num_sms) bn /= 2;
+  }
+  cp.bn = bn;
   make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn, kc);
   make_w_map(&cp.tm_w_lo, pc.w_lo, pc.cout, pc.ktot, bn, kc);
   make_w_map(&cp.tm_w_hi_half, pc.w_hi, pc.cout, pc.ktot, bn / 2, kc);

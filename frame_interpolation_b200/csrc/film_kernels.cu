@@ -295,16 +295,18 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
                                                    const sp_t* __restrict__ feat_lo, int H, int W, int C,
                                                    float* __restrict__ v_up, sp_t* __restrict__ warped_hi,
                                                    sp_t* __restrict__ warped_lo) {
-  const int G = C / 8;
-  const int64_t n = (int64_t)2 * H * W * G;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int g = (int)(i % G);
-  int64_t p = i / G;  // pixel index over [2][H][W]
-  int x = (int)(p % W);
-  int64_t q = p / W;
-  int y = (int)(q % H);
-  int d = (int)(q / H);
+  // Block = 8 x 4 pixel patch x one 64-channel chunk (8 threads per pixel): the bilinear footprints of
+  // vertically adjacent output pixels share source rows, so a 2-D patch turns those re-reads into L1 hits.
+  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 3) >> 2;
+  int bt = blockIdx.x;
+  const int tx = bt % tiles_x;
+  bt /= tiles_x;
+  const int ty = bt % tiles_y;
+  const int d = bt / tiles_y;
+  const int g = blockIdx.y * 8 + (threadIdx.x & 7);
+  const int x = tx * 8 + ((threadIdx.x >> 3) & 7), y = ty * 4 + (threadIdx.x >> 6);
+  if (x >= W || y >= H) return;
+  const int64_t p = ((int64_t)d * H + y) * W + x;  // pixel index over [2][H][W]
   float2 f = upsampled_flow(v_prev, d, Hc, Wc, H, W, y, x);
   if (g == 0) reinterpret_cast<float2*>(v_up)[p] = f;
   WarpTap t = warp_tap(y, x, f.x, f.y, H, W);
@@ -321,9 +323,8 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
 cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
                              const sp_t* feat_lo, int H, int W, int C, float* v_up,
                              sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  int64_t n = (int64_t)2 * H * W * (C / 8);
-  k_flow_warp<<<cdiv(n, 256), 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up,
-                                           warped_hi, warped_lo);
+  dim3 grid(2 * ((W + 7) / 8) * ((H + 3) / 4), C / 64);
+  k_flow_warp<<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
   return cudaGetLastError();
 }
 
@@ -335,16 +336,16 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
                                                      const sp_t* __restrict__ feat_lo, int H, int W,
                                                      int C, sp_t* __restrict__ warped_hi,
                                                      sp_t* __restrict__ warped_lo) {
-  const int G = C / 8;
-  const int64_t n = (int64_t)2 * H * W * G;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int g = (int)(i % G);
-  int64_t p = i / G;
-  int x = (int)(p % W);
-  int64_t q = p / W;
-  int y = (int)(q % H);
-  int k = (int)(q / H);
+  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 3) >> 2;  // 8 x 4 pixel patch per block (see k_flow_warp)
+  int bt = blockIdx.x;
+  const int tx = bt % tiles_x;
+  bt /= tiles_x;
+  const int ty = bt % tiles_y;
+  const int k = bt / tiles_y;
+  const int g = blockIdx.y * 8 + (threadIdx.x & 7);
+  const int x = tx * 8 + ((threadIdx.x >> 3) & 7), y = ty * 4 + (threadIdx.x >> 6);
+  if (x >= W || y >= H) return;
+  const int64_t p = ((int64_t)k * H + y) * W + x;
   // image k is warped by 0.5 * v[1 - k]
   float2 f = __ldg(reinterpret_cast<const float2*>(v) + ((int64_t)(1 - k) * H + y) * W + x);
   WarpTap t = warp_tap(y, x, f.x * 0.5f, f.y * 0.5f, H, W);
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
 
 cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
                                int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  int64_t n = (int64_t)2 * H * W * (C / 8);
-  k_fusion_warp<<<cdiv(n, 256), 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
+  dim3 grid(2 * ((W + 7) / 8) * ((H + 3) / 4), C / 64);
+  k_fusion_warp<<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
   return cudaGetLastError();
 }
 
