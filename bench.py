@@ -52,7 +52,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: one streaming
+    `nvidia-smi -lms 50` process (the recipe's clocks line), read by a thread."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -61,36 +62,46 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self._proc = None
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        try:
+            for line in self._proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx),
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+            time.sleep(0.15)     # let the first samples arrive before the timed region starts
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._proc is not None:
+            try:
+                self._proc.terminate()          # the exact process we started
+                self._proc.wait(timeout=5)
+            except Exception:
+                pass
+        if self._t is not None:
+            self._t.join(timeout=5)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
@@ -99,7 +110,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": float(max(pw)) if pw else None}
 
 
 _BEST_THREADS = None

@@ -562,7 +562,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     // tiny pyramid levels: a 17x30 level has 8 tiles but K = 17280 -- split N into smaller tiles so the
     // K-serial work spreads over more SMs (and BN <= 128 tiles use the 2-instruction product)
     auto items = [&](int b) { return (long)cp.B * cp.tiles_y * cp.tiles_x * ((pc.cout + b - 1) / b); };
-    while (bn > 64 && items(bn) < P.num_sms) bn /= 2;
+    while (bn > 64 && 2 * items(bn) <= P.num_sms) bn /= 2;  // only while under half of the SMs have work
   }
   cp.bn = bn;
   make_w_map(&cp.tm_w_hi, pc.w_hi, pc.cout, pc.ktot, bn, kc);
