@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libfilm_b200.so")
 
 EXPORTS = [
     "film_create", "film_destroy", "film_interpolate", "film_interpolate_tiled",
-    "film_interpolate_device", "film_interpolate_recursive", "film_synchronize", "film_profile", "film_set_option",
+    "film_interpolate_device", "film_interpolate_recursive", "film_host_alloc", "film_host_free",
+    "film_synchronize", "film_profile", "film_set_option",
     "film_debug_read", "film_op_table", "film_last_error", "film_version",
 ]
 
@@ -56,6 +57,10 @@ def load() -> C.CDLL:
     lib.film_interpolate_device.restype = C.c_int
     lib.film_interpolate_recursive.argtypes = [C.c_void_p, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]
     lib.film_interpolate_recursive.restype = C.c_int
+    lib.film_host_alloc.argtypes = [C.c_size_t]
+    lib.film_host_alloc.restype = C.c_void_p
+    lib.film_host_free.argtypes = [C.c_void_p]
+    lib.film_host_free.restype = None
     lib.film_synchronize.argtypes = [C.c_void_p]
     lib.film_synchronize.restype = C.c_int
     lib.film_profile.argtypes = [C.c_void_p, C.POINTER(FilmProfile)]

@@ -1465,6 +1465,19 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
   }
 }
 
+void* film_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void film_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int film_profile(film_handle* h, film_profile_t* out) {
   if (!h || !out) return FILM_ERR_ARG;
   if (h->prof.last_call_ms < 0 && h->last_plan && h->dev_events_valid) {

@@ -305,9 +305,14 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
   const int d = bt / tiles_y;
   const int g = blockIdx.y * 8 + (threadIdx.x & 7);
   const int x = tx * 8 + ((threadIdx.x >> 3) & 7), y = ty * 4 + (threadIdx.x >> 6);
-  if (x >= W || y >= H) return;
   const int64_t p = ((int64_t)d * H + y) * W + x;  // pixel index over [2][H][W]
-  float2 f = upsampled_flow(v_prev, d, Hc, Wc, H, W, y, x);
+  // the upsampled flow is computed once per pixel (by the pixel's first thread) and shared through smem
+  __shared__ float2 sflow[32];
+  const int pix = threadIdx.x >> 3;
+  if ((threadIdx.x & 7) == 0 && x < W && y < H) sflow[pix] = upsampled_flow(v_prev, d, Hc, Wc, H, W, y, x);
+  __syncthreads();
+  if (x >= W || y >= H) return;
+  const float2 f = sflow[pix];
   if (g == 0) reinterpret_cast<float2*>(v_up)[p] = f;
   WarpTap t = warp_tap(y, x, f.x, f.y, H, W);
   const int64_t src_off = (int64_t)(1 - d) * H * W * C;

@@ -51,6 +51,43 @@ def patches_to_image(patches: np.ndarray, block_shape: List[int]) -> np.ndarray:
     return np.ascontiguousarray(np.reshape(x, (1, block_height * patch_height, block_width * patch_width, channel)))
 
 
+class _PinnedPool:
+    """Pinned (page-locked) result buffers. A returned ndarray owns its buffer through a
+    finalizer: when the caller drops the array the buffer goes back to the pool (at most
+    `keep` idle buffers per size are retained, the rest are freed)."""
+
+    def __init__(self, lib, keep: int = 4):
+        self._lib = lib
+        self._keep = keep
+        self._idle = {}
+
+    def _release(self, nbytes: int, ptr: int) -> None:
+        idle = self._idle.setdefault(nbytes, [])
+        if len(idle) < self._keep:
+            idle.append(ptr)
+        else:
+            self._lib.film_host_free(C.c_void_p(ptr))
+
+    def empty(self, shape) -> np.ndarray:
+        import weakref
+        n = int(np.prod(shape))
+        nbytes = n * 4
+        idle = self._idle.get(nbytes)
+        ptr = idle.pop() if idle else self._lib.film_host_alloc(nbytes)
+        if not ptr:
+            return np.empty(shape, np.float32)           # pinned allocation failed: plain memory still works
+        buf = (C.c_float * n).from_address(ptr)
+        arr = np.ctypeslib.as_array(buf).reshape(shape)
+        weakref.finalize(buf, self._release, nbytes, ptr)  # `buf` lives as long as any view of `arr`
+        return arr
+
+    def close(self) -> None:
+        for ptrs in self._idle.values():
+            for ptr in ptrs:
+                self._lib.film_host_free(C.c_void_p(ptr))
+        self._idle = {}
+
+
 class Interpolator:
     """A class for generating interpolated frames between two input frames (B200 engine)."""
 
@@ -71,12 +108,15 @@ class Interpolator:
         self._align = align or None
         self._block_shape = block_shape or None
         self.device = int(device)
+        self._pool = _PinnedPool(self._lib)
 
     # -- lifecycle ------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self._lib.film_destroy(self._handle)
             self._handle = C.c_void_p()
+            if getattr(self, "_pool", None) is not None:
+                self._pool.close()
 
     def __del__(self):
         try:
@@ -117,7 +157,7 @@ class Interpolator:
             assert self._align > 0, 'align must be a positive number.'
         x0, x1, dt = self._prep(x0, x1, dt)
         b, h, w, _ = x0.shape
-        out = np.empty_like(x0)
+        out = self._pool.empty(x0.shape)
         st = self._lib.film_interpolate(self._handle, _fptr(x0), _fptr(x1), _fptr(dt), b, h, w,
                                         int(self._align or 0), _fptr(out))
         self._check(st)
@@ -132,7 +172,7 @@ class Interpolator:
             assert x0.shape[0] == 1, "tiled interpolation expects batch size 1"
             _, h, w, _ = x0.shape
             bh, bw = int(self._block_shape[0]), int(self._block_shape[1])
-            out = np.empty_like(x0)
+            out = self._pool.empty(x0.shape)
             st = self._lib.film_interpolate_tiled(self._handle, _fptr(x0), _fptr(x1), _fptr(dt), h, w,
                                                   int(self._align or 0), bh, bw, _fptr(out))
             self._check(st)
@@ -166,7 +206,7 @@ class Interpolator:
         assert f0.ndim == 3 and f0.shape == f1.shape and f0.shape[-1] == 3, "expected two (H, W, 3) frames"
         h, w, _ = f0.shape
         n = (1 << int(times_to_interpolate)) + 1
-        out = np.empty((n, h, w, 3), np.float32)
+        out = self._pool.empty((n, h, w, 3))
         st = self._lib.film_interpolate_recursive(self._handle, _fptr(f0), _fptr(f1), h, w,
                                                   int(self._align or 0), int(times_to_interpolate), _fptr(out))
         self._check(st)

@@ -107,6 +107,12 @@ FILM_API int film_interpolate_device(film_handle* h, const float* d_x0, const fl
 FILM_API int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W,
                                         int align, int times_to_interpolate, float* out);
 
+/* Page-locked host memory for frames (cudaHostAlloc): uploads / downloads of pinned buffers run at
+ * PCIe speed instead of through the driver's pageable staging path. The Python wrapper returns its
+ * results in pooled buffers allocated here. NULL on failure. */
+FILM_API void* film_host_alloc(size_t bytes);
+FILM_API void film_host_free(void* p);
+
 FILM_API int film_synchronize(film_handle* h);
 
 /* Fills *out with statistics of the last call on this handle. */
