@@ -51,7 +51,21 @@ __device__ __forceinline__ void split2(float x, sp_t& hi, sp_t& lo) {
 }
 
 // two floats -> packed hi pair / lo pair (little-endian: element 0 in the low half)
+#ifndef FILM_SPLIT_FP16
+// bf16: one packed convert per plane (F2FP.BF16.F32.PACK_AB), float(bf16) is a 16-bit shift -> 6
+// instructions per pair (the gather kernels are instruction-issue bound, ncu profiles/r1o)
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void split_pack2_generic(float a, float b, uint32_t& hi, uint32_t& lo) {
+#else
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+#endif
   sp_t ah, al, bh, bl;
   split2(a, ah, al);
   split2(b, bh, bl);
@@ -76,8 +90,13 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float* v
   const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+#ifndef FILM_SPLIT_FP16
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+#else
     v[2 * i] = sp_bits_to_float(hw[i] & 0xffffu) + sp_bits_to_float(lw[i] & 0xffffu);
     v[2 * i + 1] = sp_bits_to_float(hw[i] >> 16) + sp_bits_to_float(lw[i] >> 16);
+#endif
   }
 }
 

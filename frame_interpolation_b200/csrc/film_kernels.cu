@@ -276,13 +276,15 @@ __device__ __forceinline__ float lerp4(float tl, float tr, float bl, float br, f
 // gather 8 channels of a split tensor plane pair [H][W][C] (already offset to the batch)
 __device__ __forceinline__ void gather8(const sp_t* __restrict__ hi, const sp_t* __restrict__ lo,
                                         int W, int C, int c, const WarpTap& t, float* out) {
-  int64_t o00 = ((int64_t)t.y0 * W + t.x0) * C + c;
-  int64_t o01 = o00 + C, o10 = o00 + (int64_t)W * C, o11 = o10 + C;
+  const int64_t o00 = ((int64_t)t.y0 * W + t.x0) * C + c;
+  const sp_t* h0 = hi + o00;
+  const sp_t* l0 = lo + o00;
+  const int row = W * C;  // < 2^31 elements for every level
   float tl[8], tr[8], bl[8], br[8];
-  unpack8(ldg16(hi + o00), ldg16(lo + o00), tl);
-  unpack8(ldg16(hi + o01), ldg16(lo + o01), tr);
-  unpack8(ldg16(hi + o10), ldg16(lo + o10), bl);
-  unpack8(ldg16(hi + o11), ldg16(lo + o11), br);
+  unpack8(ldg16(h0), ldg16(l0), tl);
+  unpack8(ldg16(h0 + C), ldg16(l0 + C), tr);
+  unpack8(ldg16(h0 + row), ldg16(l0 + row), bl);
+  unpack8(ldg16(h0 + row + C), ldg16(l0 + row + C), br);
 #pragma unroll
   for (int j = 0; j < 8; ++j) out[j] = lerp4(tl[j], tr[j], bl[j], br[j], t.ax, t.ay);
 }
@@ -297,14 +299,11 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
                                                    sp_t* __restrict__ warped_lo) {
   // Block = 8 x 4 pixel patch x one 64-channel chunk (8 threads per pixel): the bilinear footprints of
   // vertically adjacent output pixels share source rows, so a 2-D patch turns those re-reads into L1 hits.
-  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 3) >> 2;
-  int bt = blockIdx.x;
-  const int tx = bt % tiles_x;
-  bt /= tiles_x;
-  const int ty = bt % tiles_y;
-  const int d = bt / tiles_y;
-  const int g = blockIdx.y * 8 + (threadIdx.x & 7);
-  const int x = tx * 8 + ((threadIdx.x >> 3) & 7), y = ty * 4 + (threadIdx.x >> 6);
+  // grid = (tiles_x, tiles_y, 2 * C/64): no integer divisions in the index math
+  const int nchunk = C >> 6;
+  const int d = blockIdx.z / nchunk;
+  const int g = (blockIdx.z - d * nchunk) * 8 + (threadIdx.x & 7);
+  const int x = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7), y = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int64_t p = ((int64_t)d * H + y) * W + x;  // pixel index over [2][H][W]
   // the upsampled flow is computed once per pixel (by the pixel's first thread) and shared through smem
   __shared__ float2 sflow[32];
@@ -328,7 +327,7 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
 cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
                              const sp_t* feat_lo, int H, int W, int C, float* v_up,
                              sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  dim3 grid(2 * ((W + 7) / 8) * ((H + 3) / 4), C / 64);
+  dim3 grid((W + 7) / 8, (H + 3) / 4, 2 * (C / 64));
   k_flow_warp<<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
   return cudaGetLastError();
 }
@@ -341,14 +340,11 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
                                                      const sp_t* __restrict__ feat_lo, int H, int W,
                                                      int C, sp_t* __restrict__ warped_hi,
                                                      sp_t* __restrict__ warped_lo) {
-  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 3) >> 2;  // 8 x 4 pixel patch per block (see k_flow_warp)
-  int bt = blockIdx.x;
-  const int tx = bt % tiles_x;
-  bt /= tiles_x;
-  const int ty = bt % tiles_y;
-  const int k = bt / tiles_y;
-  const int g = blockIdx.y * 8 + (threadIdx.x & 7);
-  const int x = tx * 8 + ((threadIdx.x >> 3) & 7), y = ty * 4 + (threadIdx.x >> 6);
+  // 8 x 4 pixel patch per block, grid = (tiles_x, tiles_y, 2 * C/64) (see k_flow_warp)
+  const int nchunk = C >> 6;
+  const int k = blockIdx.z / nchunk;
+  const int g = (blockIdx.z - k * nchunk) * 8 + (threadIdx.x & 7);
+  const int x = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7), y = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (x >= W || y >= H) return;
   const int64_t p = ((int64_t)k * H + y) * W + x;
   // image k is warped by 0.5 * v[1 - k]
@@ -366,7 +362,7 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
 
 cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
                                int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  dim3 grid(2 * ((W + 7) / 8) * ((H + 3) / 4), C / 64);
+  dim3 grid((W + 7) / 8, (H + 3) / 4, 2 * (C / 64));
   k_fusion_warp<<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
   return cudaGetLastError();
 }
