@@ -382,7 +382,7 @@ cudaError_t conv3x3_tc_configure() {
 #define FILM_CFG(BN, KC)                                                                                     \
   e = cudaFuncSetAttribute(k_conv3x3_tc<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);   \
   if (e != cudaSuccess) return e;
-  FILM_CFG(32, 64) FILM_CFG(64, 64) FILM_CFG(128, 64) FILM_CFG(256, 64) FILM_CFG(32, 32)
+  FILM_CFG(32, 64) FILM_CFG(64, 64) FILM_CFG(128, 64) FILM_CFG(256, 64) FILM_CFG(32, 32) FILM_CFG(64, 32)
 #undef FILM_CFG
   return cudaSuccess;
 }
@@ -390,9 +390,10 @@ cudaError_t conv3x3_tc_configure() {
 cudaError_t launch_conv3x3_tc(const ConvProblem* d_prob, const ConvProblem& h, cudaStream_t st) {
   const int bn = h.bn;
   const int smem = smem_bytes_for(h, bn);
-  if (h.kchunk == 32) {
-    if (bn != 32) return cudaErrorInvalidValue;  // only the 32 -> 32 flow convs use 32-channel K blocks
-    k_conv3x3_tc<32, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);
+  if (h.kchunk == 32) {  // 32-channel K blocks: the 32 -> 32 flow convs and the 3(32) -> 64 first conv
+    if (bn == 32) k_conv3x3_tc<32, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);
+    else if (bn == 64) k_conv3x3_tc<64, 32><<<h.v2_grid, kThreads, smem, st>>>(d_prob);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
   }
   switch (bn) {

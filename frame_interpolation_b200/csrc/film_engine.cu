@@ -258,7 +258,8 @@ static std::vector<int> side_map(int C) {
 struct Model {
   std::vector<void*> allocs;
   float *conv0_w = nullptr, *conv0_b = nullptr;  // cfeat_conv_0 [27][64]
-  PackedConv fe[8];                              // fe[1..7]
+  PackedConv fe[8];                              // fe[0] = 1x1 over im2col channels, fe[1..7] = 3x3
+  PackedConv fe0_3x3;                            // cfeat_conv_0 as a 3x3 conv over a 32-channel-padded image
   PackedConv flow[4][3];                         // predictor p, 3x3 conv k
   PackedConv flow_c3[4];                         // predictor p, 1x1 conv_3 (tensor-core, fused head)
   float *flow_w3[4], *flow_b3[4], *flow_w4[4], *flow_b4[4];
@@ -285,6 +286,9 @@ struct Model {
       k0.dims = {1, 1, 27, 64};
       fe[0] = pack_conv(k0, get_tensor(w, fe_pre + "0/bias", {64}), {iota_map(0, 27, 32)},
                         {TapSpec{0, 0, {{0, 0}}}}, allocs, 32);
+      // ... or directly as a 3x3 conv whose 32-channel K block holds the 3 image channels + 29 zeros
+      fe0_3x3 = pack_conv(get_tensor(w, fe_pre + "0/kernel", {3, 3, 3, 64}), get_tensor(w, fe_pre + "0/bias", {64}),
+                          {iota_map(0, 3, 32)}, taps_3x3(), allocs, 32);
     }
     int cin = 64;
     for (int k = 1; k < 8; ++k) {
@@ -512,7 +516,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   const int kc = pc.kchunk;
   cp.kchunk = kc;
   const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1 &&
-                  (kc == kChunk || pc.cout <= 32);
+                  (kc == kChunk || pc.cout <= 64);
   int box_h, box_w;
   // CTA-pair kernel: large levels only (it needs 16x8 tiles and enough tile pairs to fill the SM pairs)
   const bool want_pair = v2 && P.conv3x3_2cta &&
@@ -690,8 +694,18 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     for (int j = 0; j < depth; ++j) {
       const int r = i + j, c = kFilters << j;
       SplitBuf* t1 = P.split(2, Hs[r], Ws[r], c);
-      if (j == 0 && P.conv_impl == 0) {
-        // cfeat_conv_0 on the tensor cores: im2col-lite (27 -> 32 channels) + a 1x1 conv, K = 32
+      if (j == 0 && P.conv_impl == 0 && P.conv3x3_v2) {
+        // cfeat_conv_0 on the persistent 3x3 tensor-core kernel: the image is widened to a 32-channel
+        // split tensor (3 real channels), K = 9 taps x one 32-channel block
+        const float* im = img[i];
+        const int hh = Hs[r], ww = Ws[r];
+        SplitBuf* im32 = P.split(2, hh, ww, 32);
+        P.add_op(2, "fe_split32@L" + std::to_string(r),
+                 [=](cudaStream_t st) { return launch_image_to_split32(im, 2, hh, ww, im32->hi, im32->lo, st); }, 0,
+                 2.0 * hh * ww * (12 + 32.0));
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe0_3x3, {{im32, 0}}, 1, t1, 0);
+      } else if (j == 0 && P.conv_impl == 0) {
+        // generic-kernel variant: im2col-lite (27 -> 32 channels) + a 1x1 conv, K = 32
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
         SplitBuf* col = P.split(2, hh, ww, 32);

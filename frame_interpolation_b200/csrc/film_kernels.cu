@@ -157,6 +157,25 @@ __global__ void __launch_bounds__(256) k_im2col3x3(const float* __restrict__ img
   *reinterpret_cast<uint4*>(out_lo + p * 32 + g * 8) = l;
 }
 
+// [B][H][W][3] fp32 image -> first 8 channels of a [B][H][W][32] split tensor (channels 3..31 stay at
+// their initial zero): the input of cfeat_conv_0 when it runs on the persistent 3x3 tensor-core kernel.
+__global__ void __launch_bounds__(256) k_image_to_split32(const float* __restrict__ img, int64_t npix,
+                                                          sp_t* __restrict__ out_hi, sp_t* __restrict__ out_lo) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float v[8] = {__ldg(img + p * 3), __ldg(img + p * 3 + 1), __ldg(img + p * 3 + 2), 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4 h, l;
+  pack8(v, h, l);
+  *reinterpret_cast<uint4*>(out_hi + p * 32) = h;
+  *reinterpret_cast<uint4*>(out_lo + p * 32) = l;
+}
+
+cudaError_t launch_image_to_split32(const float* img, int B, int H, int W, sp_t* out_hi, sp_t* out_lo, cudaStream_t st) {
+  int64_t npix = (int64_t)B * H * W;
+  k_image_to_split32<<<cdiv(npix, 256), 256, 0, st>>>(img, npix, out_hi, out_lo);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_im2col3x3(const float* img, int B, int H, int W, sp_t* out_hi, sp_t* out_lo, cudaStream_t st) {
   int64_t n = (int64_t)B * H * W * 4;
   k_im2col3x3<<<cdiv(n, 256), 256, 0, st>>>(img, B, H, W, out_hi, out_lo);

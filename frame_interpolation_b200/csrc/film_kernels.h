@@ -19,6 +19,9 @@ cudaError_t launch_conv0_c3(const float* img, int B, int H, int W, const float* 
 // (27 tap x channel values in HWIO order + 5 zero channels, zero outside the image).
 cudaError_t launch_im2col3x3(const float* img, int B, int H, int W, sp_t* out_hi, sp_t* out_lo, cudaStream_t st);
 
+// [B][H][W][3] fp32 -> channels 0..7 of a zero-initialised [B][H][W][32] split tensor (3 real channels).
+cudaError_t launch_image_to_split32(const float* img, int B, int H, int W, sp_t* out_hi, sp_t* out_lo, cudaStream_t st);
+
 // feature_extractor.py:138-146 -- 2x2/2 VALID average pool of a channel slice of a split tensor.
 cudaError_t launch_act_pool(const sp_t* in_hi, const sp_t* in_lo, int in_C, int in_c_off, int B,
                             int H, int W, int Cn, sp_t* out_hi, sp_t* out_lo, int out_C,
