@@ -145,8 +145,11 @@ def from_named_arrays(arrays: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]
     if order and len(order) != len(names):
         raise ValueError(f"expected {len(names)} fusion convs, found {len(order)}")
     for idx, nm in zip(order, names):
-        out[nm + "/kernel"] = fusion_layers[idx]["kernel"]
-        out[nm + "/bias"] = fusion_layers[idx]["bias"]
+        layer = fusion_layers[idx]
+        if "kernel" not in layer or "bias" not in layer:
+            raise ValueError(f"fusion conv #{idx} is missing its kernel or bias")
+        out[nm + "/kernel"] = layer["kernel"]
+        out[nm + "/bias"] = layer["bias"]
     missing = set(table) - set(out)
     if missing:
         raise ValueError(f"missing variables: {sorted(missing)[:5]} ...")
