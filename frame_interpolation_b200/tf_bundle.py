@@ -322,3 +322,10 @@ def write_bundle(prefix: str, tensors: Mapping[str, np.ndarray], with_crc: bool 
     out.extend(footer)
     with open(prefix + ".index", "wb") as f:
         f.write(bytes(out))
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) != 3:
+        raise SystemExit("usage: python -m frame_interpolation_b200.tf_bundle <saved_model_dir> <out.filmw>")
+    print(convert_saved_model(sys.argv[1], sys.argv[2]))
