@@ -107,6 +107,35 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
   split_pack2(v[6], v[7], h.w, l.w);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): 16 channels of one plane per instruction, i.e.
+// one whole 32-byte sector per thread -- the strided per-pixel epilogue stores and the gathers are
+// instruction-issue / LSU bound, not bandwidth bound.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+// 16 consecutive channels: pack to (hi 32 B, lo 32 B) and store
+__device__ __forceinline__ void pack_store16(const float* v, sp_t* hi_dst, sp_t* lo_dst) {
+  uint4 h0, l0, h1, l1;
+  pack8(v, h0, l0);
+  pack8(v + 8, h1, l1);
+  st256(hi_dst, h0, h1);
+  st256(lo_dst, l0, l1);
+}
+__device__ __forceinline__ void load_unpack16(const sp_t* hi_src, const sp_t* lo_src, float* v) {
+  uint4 h0, h1, l0, l1;
+  ld256_nc(hi_src, h0, h1);
+  ld256_nc(lo_src, l0, l1);
+  unpack8(h0, l0, v);
+  unpack8(h1, l1, v + 8);
+}
+
 __device__ __forceinline__ float leaky(float x) { return x >= 0.f ? x : x * kLeaky; }
 
 }  // namespace film

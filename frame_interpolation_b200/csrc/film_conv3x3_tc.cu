@@ -280,34 +280,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         } else {
           tmem_ld_wait();
         }
+        {
+          float f[16];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = __uint_as_float(v[g * 8 + j]) + bias_smem[n0 + cc * 16 + g * 8 + j];
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(v[j]) + bias_smem[n0 + cc * 16 + j];
             f[j] = act ? leaky(x) : x;
           }
-          if (valid) {
-            uint4 h, l;
-            pack8(f, h, l);
-            *reinterpret_cast<uint4*>(oh + cc * 16 + g * 8) = h;
-            *reinterpret_cast<uint4*>(ol + cc * 16 + g * 8) = l;
-          }
+          if (valid) pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
           if (do_pool) {
-            float pf[8];
+            float pf[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const float a = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
               pf[j] = (a + __shfl_xor_sync(0xffffffffu, a, 8)) * 0.25f;
             }
             // lanes with even tile row and even tile column own the pooled pixel (H, W are even)
             if (valid && !(lane & 1) && !(lane & 8)) {
               const int64_t ppix = ((int64_t)b * (out_H >> 1) + (py >> 1)) * (out_W >> 1) + (px >> 1);
-              uint4 h, l;
-              pack8(pf, h, l);
-              *reinterpret_cast<uint4*>(pool_hi + ppix * pool_C + n0 + cc * 16 + g * 8) = h;
-              *reinterpret_cast<uint4*>(pool_lo + ppix * pool_C + n0 + cc * 16 + g * 8) = l;
+              pack_store16(pf, pool_hi + ppix * pool_C + n0 + cc * 16, pool_lo + ppix * pool_C + n0 + cc * 16);
             }
           }
         }

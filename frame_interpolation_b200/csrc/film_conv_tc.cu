@@ -241,17 +241,14 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
         }
         if (valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+          for (int g = 0; g < 2; ++g) {
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[g * 8 + j]) + bias_smem[cc * 32 + g * 8 + j];
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(v[g * 16 + j]) + bias_smem[cc * 32 + g * 16 + j];
               f[j] = act ? leaky(x) : x;
             }
-            uint4 h, l;
-            pack8(f, h, l);
-            *reinterpret_cast<uint4*>(oh + cc * 32 + g * 8) = h;
-            *reinterpret_cast<uint4*>(ol + cc * 32 + g * 8) = l;
+            pack_store16(f, oh + cc * 32 + g * 16, ol + cc * 32 + g * 16);
           }
         }
       }

@@ -308,6 +308,27 @@ __device__ __forceinline__ void gather8(const sp_t* __restrict__ hi, const sp_t*
   for (int j = 0; j < 8; ++j) out[j] = lerp4(tl[j], tr[j], bl[j], br[j], t.ax, t.ay);
 }
 
+// gather 16 channels with 256-bit loads (two taps at a time to bound the live registers)
+__device__ __forceinline__ void gather16(const sp_t* __restrict__ hi, const sp_t* __restrict__ lo,
+                                         int W, int C, int c, const WarpTap& t, float* out) {
+  const int64_t o00 = ((int64_t)t.y0 * W + t.x0) * C + c;
+  const sp_t* h0 = hi + o00;
+  const sp_t* l0 = lo + o00;
+  const int row = W * C;
+  float a[16], b[16], top[16];
+  load_unpack16(h0, l0, a);
+  load_unpack16(h0 + C, l0 + C, b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) top[j] = t.ax * (b[j] - a[j]) + a[j];
+  load_unpack16(h0 + row, l0 + row, a);
+  load_unpack16(h0 + row + C, l0 + row + C, b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float bot = t.ax * (b[j] - a[j]) + a[j];
+    out[j] = t.ay * (bot - top[j]) + top[j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pyramid_flow_estimator.py:154-157  flow upsample (x2 magnitude) fused with the feature warp
 // ------------------------------------------------------------------------------------------
@@ -318,35 +339,32 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
                                                    sp_t* __restrict__ warped_lo) {
   // Block = 8 x 4 pixel patch x one 64-channel chunk (8 threads per pixel): the bilinear footprints of
   // vertically adjacent output pixels share source rows, so a 2-D patch turns those re-reads into L1 hits.
+  // Block = 8 x 8 pixel patch x one 64-channel chunk, 4 threads per pixel x 16 channels (256-bit accesses);
   // grid = (tiles_x, tiles_y, 2 * C/64): no integer divisions in the index math
   const int nchunk = C >> 6;
   const int d = blockIdx.z / nchunk;
-  const int g = (blockIdx.z - d * nchunk) * 8 + (threadIdx.x & 7);
-  const int x = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int c = (blockIdx.z - d * nchunk) * 64 + (threadIdx.x & 3) * 16;
+  const int x = blockIdx.x * 8 + ((threadIdx.x >> 2) & 7), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int64_t p = ((int64_t)d * H + y) * W + x;  // pixel index over [2][H][W]
   // the upsampled flow is computed once per pixel (by the pixel's first thread) and shared through smem
-  __shared__ float2 sflow[32];
-  const int pix = threadIdx.x >> 3;
-  if ((threadIdx.x & 7) == 0 && x < W && y < H) sflow[pix] = upsampled_flow(v_prev, d, Hc, Wc, H, W, y, x);
+  __shared__ float2 sflow[64];
+  const int pix = threadIdx.x >> 2;
+  if ((threadIdx.x & 3) == 0 && x < W && y < H) sflow[pix] = upsampled_flow(v_prev, d, Hc, Wc, H, W, y, x);
   __syncthreads();
   if (x >= W || y >= H) return;
   const float2 f = sflow[pix];
-  if (g == 0) reinterpret_cast<float2*>(v_up)[p] = f;
+  if (c == 0) reinterpret_cast<float2*>(v_up)[p] = f;
   WarpTap t = warp_tap(y, x, f.x, f.y, H, W);
   const int64_t src_off = (int64_t)(1 - d) * H * W * C;
-  float o[8];
-  gather8(feat_hi + src_off, feat_lo + src_off, W, C, g * 8, t, o);
-  uint4 h, l;
-  pack8(o, h, l);
-  int64_t oo = p * C + g * 8;
-  *reinterpret_cast<uint4*>(warped_hi + oo) = h;
-  *reinterpret_cast<uint4*>(warped_lo + oo) = l;
+  float o[16];
+  gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
+  pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
 }
 
 cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
                              const sp_t* feat_lo, int H, int W, int C, float* v_up,
                              sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  dim3 grid((W + 7) / 8, (H + 3) / 4, 2 * (C / 64));
+  dim3 grid((W + 7) / 8, (H + 7) / 8, 2 * (C / 64));
   k_flow_warp<<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
   return cudaGetLastError();
 }
@@ -359,29 +377,25 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
                                                      const sp_t* __restrict__ feat_lo, int H, int W,
                                                      int C, sp_t* __restrict__ warped_hi,
                                                      sp_t* __restrict__ warped_lo) {
-  // 8 x 4 pixel patch per block, grid = (tiles_x, tiles_y, 2 * C/64) (see k_flow_warp)
+  // 8 x 8 pixel patch x 64-channel chunk per block, 16 channels per thread (see k_flow_warp)
   const int nchunk = C >> 6;
   const int k = blockIdx.z / nchunk;
-  const int g = (blockIdx.z - k * nchunk) * 8 + (threadIdx.x & 7);
-  const int x = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int c = (blockIdx.z - k * nchunk) * 64 + (threadIdx.x & 3) * 16;
+  const int x = blockIdx.x * 8 + ((threadIdx.x >> 2) & 7), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
   const int64_t p = ((int64_t)k * H + y) * W + x;
   // image k is warped by 0.5 * v[1 - k]
   float2 f = __ldg(reinterpret_cast<const float2*>(v) + ((int64_t)(1 - k) * H + y) * W + x);
   WarpTap t = warp_tap(y, x, f.x * 0.5f, f.y * 0.5f, H, W);
   const int64_t src_off = (int64_t)k * H * W * C;
-  float o[8];
-  gather8(feat_hi + src_off, feat_lo + src_off, W, C, g * 8, t, o);
-  uint4 h, l;
-  pack8(o, h, l);
-  int64_t oo = p * C + g * 8;
-  *reinterpret_cast<uint4*>(warped_hi + oo) = h;
-  *reinterpret_cast<uint4*>(warped_lo + oo) = l;
+  float o[16];
+  gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
+  pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
 }
 
 cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
                                int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
-  dim3 grid((W + 7) / 8, (H + 3) / 4, 2 * (C / 64));
+  dim3 grid((W + 7) / 8, (H + 7) / 8, 2 * (C / 64));
   k_fusion_warp<<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
   return cudaGetLastError();
 }
