@@ -272,3 +272,26 @@ def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     assert np.abs(out - default(x0, x1, DT)).max() < 1e-4
     eng.close()
     default.close()
+
+
+def test_results_live_in_distinct_pinned_buffers(engine):
+    """Results are returned in pooled page-locked buffers; a buffer must never be recycled while the
+    caller still holds the array (or a view of it)."""
+    import gc
+    a0, a1 = synthetic.frame_pair(64, 64, seed=1, n_waves=4)
+    b0, b1 = synthetic.frame_pair(64, 64, seed=2, n_waves=4)
+    ra = engine(a0, a1, DT)
+    keep = ra.copy()
+    view = ra[0, 10:20]
+    rb = engine(b0, b1, DT)
+    assert ra.ctypes.data != rb.ctypes.data
+    np.testing.assert_array_equal(ra, keep)
+    del ra
+    gc.collect()
+    rc = engine(b0, b1, DT)                      # the buffer behind `view` is still owned by the caller
+    np.testing.assert_array_equal(view, keep[0, 10:20])
+    np.testing.assert_array_equal(rc, rb)
+    del view, rb, rc
+    gc.collect()
+    for _ in range(8):                           # steady state: buffers are recycled, results stay right
+        np.testing.assert_array_equal(engine(a0, a1, DT), keep)
