@@ -1437,6 +1437,8 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
           try {
             run_plan(h, P, h->stream);
           } catch (const Error& err) {
+            cudaStreamSynchronize(h->stream);
+            for (auto& fe : frame_events) cudaEventDestroy(fe.second);
             cudaFree(seq);
             throw;
           }
