@@ -26,8 +26,10 @@ struct ConvSrc {
   const sp_t* lo;
   int C;       // channel stride of the tensor (allocated channels)
   int c_off;   // first channel consumed
-  int nchunk;  // number of 64-channel chunks consumed
-  int pad_;
+  int nchunk;  // number of K-block chunks consumed
+  int ksteps;  // 16-channel k-steps issued per chunk (< kchunk/16 when the tail channels of every chunk are
+               // zero padding, e.g. the 10-of-64 "side" source): skipping is exact.  Honoured by the persistent
+               // 3x3 kernels; the generic kernel issues every k-step
 };
 
 struct alignas(64) ConvProblem {

@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "film_conv.h"
 #include "film_tc_ptx.cuh"
 
@@ -113,6 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     for (int s = 0; s < kMaxSrc; ++s) {
       src_tab[2 * s] = s < nsrc ? prob->src[s].nchunk : 0;
       src_tab[2 * s + 1] = s < nsrc ? prob->src[s].c_off : 0;
+      src_tab[2 * kMaxSrc + s] = s < nsrc ? prob->src[s].ksteps : 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -205,61 +208,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tc_fence_after();
       }
       const int nab = nkb / 3;
-      uint32_t ia = 0, iw = 0, it = 0;
-      for (int item = item0; item < nitems; item += item_step, ++it) {
-        const uint32_t acc = it & 1u;
-        mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccCols;
-        int kb = 0;
-        for (int ab = 0; ab < nab; ++ab) {
-          const int st = ia % NA;
-          mbar_wait(a_full(st), (ia / NA) & 1u);
+      // two instantiations of the item loop: see film_conv3x3_tc.cu (partial sources skip zero k-steps)
+      bool any_partial = false;
+      for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
+      auto run_items = [&](auto partial_tag) {
+        constexpr bool kPartial = decltype(partial_tag)::value;
+        uint32_t ia = 0, iw = 0, it = 0;
+        for (int item = item0; item < nitems; item += item_step, ++it) {
+          const uint32_t acc = it & 1u;
+          mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t sa = a_base + st * kAStage;
-          for (int dy = 0; dy < 3; ++dy, ++kb) {
-            uint32_t sw;
-            int ws = 0;
-            if (resident) {
-              sw = w_base + kb * kWTap;
-            } else {
-              ws = iw % NW;
-              mbar_wait(w_full(ws), (iw / NW) & 1u);
-              tc_fence_after();
-              sw = w_base + ws * kWTap;
-            }
-            if (elect_one()) {
-              const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
-              const uint32_t first = (kb == 0) ? 0u : 1u;
-              if constexpr (kFused) {
-                // region X (leader: W_hi, peer: W_lo) is the 2*BN-row operand; region Y = halves of W_hi
-                const uint64_t w_x = make_desc_kc<KC>(sw), w_y = make_desc_kc<KC>(sw + kWFull);
-#pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                  umma_2sm(d_tmem, a_hi + adv, w_x + adv, idesc2, k == 0 ? first : 1u);
-                  umma_2sm(d_tmem, a_lo + adv, w_y + adv, idesc, 1u);
-                }
-              } else {
-                const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
-#pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                  umma_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
-                  umma_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-                  umma_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
-                }
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          int kb = 0;
+          [[maybe_unused]] int src_i = 0, src_left = src_tab[0] * 3;  // activation stages left in the current source
+          for (int ab = 0; ab < nab; ++ab) {
+            [[maybe_unused]] int ksteps = KC / 16;
+            if constexpr (kPartial) {  // all-zero tail k-steps are skipped (exact)
+              while (src_left == 0) {
+                ++src_i;
+                src_left = src_tab[2 * src_i] * 3;
               }
-              if (!resident) umma_commit_2sm_mc(w_empty(ws));
-              if (dy == 2) umma_commit_2sm_mc(a_empty(st));
-              if (dy == 2 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+              --src_left;
+              ksteps = src_tab[2 * kMaxSrc + src_i];
             }
-            __syncwarp();
-            if (!resident) ++iw;
+            const int st = ia % NA;
+            mbar_wait(a_full(st), (ia / NA) & 1u);
+            tc_fence_after();
+            const uint32_t sa = a_base + st * kAStage;
+            for (int dy = 0; dy < 3; ++dy, ++kb) {
+              uint32_t sw;
+              int ws = 0;
+              if (resident) {
+                sw = w_base + kb * kWTap;
+              } else {
+                ws = iw % NW;
+                mbar_wait(w_full(ws), (iw / NW) & 1u);
+                tc_fence_after();
+                sw = w_base + ws * kWTap;
+              }
+              if (elect_one()) {
+                const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
+                const uint32_t first = (kb == 0) ? 0u : 1u;
+                if constexpr (kFused) {
+                  // region X (leader: W_hi, peer: W_lo) is the 2*BN-row operand; region Y = halves of W_hi
+                  const uint64_t w_x = make_desc_kc<KC>(sw), w_y = make_desc_kc<KC>(sw + kWFull);
+  #pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    if constexpr (kPartial) {
+                      if (k >= ksteps) break;
+                    }
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    umma_2sm(d_tmem, a_hi + adv, w_x + adv, idesc2, k == 0 ? first : 1u);
+                    umma_2sm(d_tmem, a_lo + adv, w_y + adv, idesc, 1u);
+                  }
+                } else {
+                  const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
+  #pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    if constexpr (kPartial) {
+                      if (k >= ksteps) break;
+                    }
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    umma_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
+                    umma_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                    umma_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+                  }
+                }
+                if (!resident) umma_commit_2sm_mc(w_empty(ws));
+                if (dy == 2) umma_commit_2sm_mc(a_empty(st));
+                if (dy == 2 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+              }
+              __syncwarp();
+              if (!resident) ++iw;
+            }
+            ++ia;
           }
-          ++ia;
         }
-      }
+      };
+      if (any_partial) run_items(std::true_type{});
+      else run_items(std::false_type{});
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================

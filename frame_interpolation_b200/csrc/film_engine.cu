@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -144,6 +145,7 @@ struct PackedConv {
   int cout = 0, ktot = 0, cin_ref = 0;
   int kchunk = kChunk;          // channels per K block (64, or 32 for the 32-channel layers)
   std::vector<int> src_chunks;  // K-block chunks per source
+  std::vector<int> src_ksteps;  // 16-channel k-steps per chunk that hold at least one real channel
   int ntaps = 0;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
 };
@@ -172,6 +174,12 @@ static PackedConv pack_conv(const HostTensor& kernel, const HostTensor& bias,
   for (auto& sm : src_maps) {
     if (sm.size() % chunk) throw Error{FILM_ERR_WEIGHTS, "source channel map not a multiple of the K chunk"};
     pc.src_chunks.push_back((int)sm.size() / chunk);
+    // k-steps whose 16 channels are zero padding in EVERY chunk of the source are never issued (exact):
+    // the 10-of-64 "side" source runs 1 of 4 k-steps, the 3-of-32 image block 1 of 2
+    int ks = 1;
+    for (size_t i = 0; i < sm.size(); ++i)
+      if (sm[i] >= 0) ks = std::max(ks, (int)(i % chunk) / 16 + 1);
+    pc.src_ksteps.push_back(ks);
     ktot += (int)sm.size() * (int)taps.size();
   }
   pc.ktot = ktot;
@@ -546,6 +554,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     cp.src[s].C = b->C;
     cp.src[s].c_off = sources[s].c_off;
     cp.src[s].nchunk = pc.src_chunks[s];
+    cp.src[s].ksteps = pc.src_ksteps[s];
     if (sources[s].c_off + pc.src_chunks[s] * kc > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
     make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w, kc);
     make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w, kc);
@@ -614,7 +623,10 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   const size_t idx = P.h_probs.size();
   P.h_probs.push_back(cp);
   // issued tensor-core work: 3 passes over the padded K and the padded tile grid
-  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * (double)pc.ktot *
+  double k_issued = 0;  // skipped all-zero k-steps are not issued work
+  for (size_t si = 0; si < pc.src_chunks.size(); ++si)
+    k_issued += (double)pc.src_chunks[si] * pc.ntaps * ((v2 || pair) ? pc.src_ksteps[si] * 16 : pc.kchunk);
+  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * k_issued *
                  (double)(((pc.cout + bn - 1) / bn) * bn);
   if (no_op) return idx;  // the caller launches this problem as part of a group
   Plan* pp = &P;
