@@ -79,6 +79,10 @@ struct alignas(64) ConvProblem {
   int pool_C;
   int group;              // generic kernel: number of consecutive problems launched as grid.z
   int pair;               // 1: run on the CTA-pair (cta_group::2) persistent kernel (film_conv3x3_tc2.cu)
+  int halo;               // persistent 3x3 kernels, 16x8 tiles, 64-channel chunks: 1 = ONE (64 ch, 10 px, 18 rows)
+                          // halo box per chunk serves all nine taps (UMMA descriptors start at pixel granularity,
+                          // SBO = 1280 B; tools/ubench/desc_offset_test.cu); 0 = three dx-shifted 8-px boxes.
+                          // Set to 1 by the engine to ALLOW it; the plan functions keep or clear it.
   int bn;                 // N tile (32/64/128/256): conv_tc_block_n(cout), or smaller on tiny levels so that
                           // a K-serial problem spreads over more SMs
 };

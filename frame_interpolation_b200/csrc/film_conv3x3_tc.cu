@@ -41,6 +41,17 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 // 16x8 has the smallest halo (18/16); 8x16 and 4x32 exist to avoid wave quantisation on small levels.
 __host__ __device__ constexpr int a_plane_bytes(int kc, int th, int tw) { return (th + 2) * tw * kc * 2; }
 __host__ __device__ constexpr int a_stage_bytes(int kc, int th, int tw) { return 2 * a_plane_bytes(kc, th, tw); }
+// Wide-halo mode (16x8 tiles, 64-channel chunks): ONE box (64 ch, 10 px, 18 rows) per plane and chunk serves
+// all nine taps -- the UMMA descriptor of tap (dy, dx) starts (dy * 10 + dx) * 128 B into the box and steps
+// 1280 B between 8-row groups (hardware check: tools/ubench/desc_offset_test.cu).  2.4x less L2 -> smem
+// activation traffic than the three dx-shifted boxes.
+constexpr int kHaloW = 10, kHaloRows = 18;
+constexpr int kHaloBox = kHaloRows * kHaloW * 64 * 2;           // 23,040 bytes written per plane
+constexpr int kHaloPlane = (kHaloBox + 1023) & ~1023;           // planes start on a swizzle-atom boundary
+constexpr int kHaloStage = 2 * kHaloPlane;
+__host__ __device__ constexpr int a_stage_bytes_h(int kc, int th, int tw, int halo) {
+  return halo ? kHaloStage : a_stage_bytes(kc, th, tw);
+}
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
@@ -53,7 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
   extern __shared__ uint8_t smem_raw[];
   constexpr int kWTap = BN * KC * 2 * 2;
   const int kTileH = prob->tile_h, kTileW = prob->tile_w;
-  const int kAPlane = a_plane_bytes(KC, kTileH, kTileW), kAStage = a_stage_bytes(KC, kTileH, kTileW);
+  const bool halo = KC == 64 && prob->halo != 0;   // plan guarantees 16x8 tiles
+  const int kAPlane = halo ? kHaloPlane : a_plane_bytes(KC, kTileH, kTileW);
+  const int kAStage = halo ? kHaloStage : a_stage_bytes(KC, kTileH, kTileW);
   const int kRowStep = kTileW * KC * 2;  // one tile row of pixels = tile_w/8 swizzle atoms
   constexpr bool kFused = BN <= 128;
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
@@ -141,9 +154,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
               // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the (tile_w + 2)-px-wide halo
               const int cc = src_tab[2 * s + 1] + ch * KC;
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 - 1, ny0 - 1, nb);
-              tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 + 1, ny0 - 1, nb);
               tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 - 1, ny0 - 1, nb);
-              tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 + 1, ny0 - 1, nb);
+              if (!halo) {  // (the wide box already spans the halo)
+                tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 + 1, ny0 - 1, nb);
+                tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 + 1, ny0 - 1, nb);
+              }
             }
         }
         __syncwarp();
@@ -154,19 +169,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
         const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
         for (int ch = 0; ch < nchunk; ++ch) {
-          for (int dx = 0; dx < 3; ++dx) {
+          const int nst = halo ? 1 : 3;   // activation stages of this chunk: one wide halo box or three dx boxes
+          for (int dx = 0; dx < nst; ++dx) {
             const int st = ia % NA;
             mbar_wait(tail + 8u * (kMaxRing + st), ((ia / NA) & 1u) ^ 1u);
             if (elect_one()) {
               const uint32_t sa = a_base + st * kAStage, bar = tail + 8u * st;
-              mbar_expect_tx(bar, kAStage);
+              mbar_expect_tx(bar, halo ? 2u * kHaloBox : (uint32_t)kAStage);
               tma_load_4d(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
               tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
             }
             __syncwarp();
             ++ia;
             if (!resident) {
-              for (int dy = 0; dy < 3; ++dy, ++kb) {
+              const int ntap = halo ? 9 : 3;   // weight taps consumed against this activation stage
+              for (int t = 0; t < ntap; ++t, ++kb) {
                 const int ws = iw % NW;
                 mbar_wait(tail + 8u * (3 * kMaxRing + ws), ((iw / NW) & 1u) ^ 1u);
                 if (elect_one()) {
@@ -191,14 +208,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       mbar_wait(tail + 8u * (2 * kMaxRing), 0);
       tc_fence_after();
     }
-    const int nab = nkb / 3;  // activation stages per tile
     // The item loop is instantiated twice: sources whose trailing 16-channel k-steps are zero padding in every
     // chunk (ConvSrc::ksteps < KC/16: the 10-of-64 "side" source, the 3-of-32 image block) skip those k-steps;
     // every other layer runs the loop without the bookkeeping (the issuing warp is issue-bound).
     bool any_partial = false;
     for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
-    auto run_items = [&](auto partial_tag) {
+    // Halo mode: one activation stage per chunk carries all nine taps; tap t = 3*dx + dy (the K order of the
+    // packed weights) reads the box at byte offset (dy * 10 + dx) * 128, 8-row groups 1280 B apart.
+    auto run_items = [&](auto partial_tag, auto halo_tag) {
       constexpr bool kPartial = decltype(partial_tag)::value;
+      constexpr bool kHalo = decltype(halo_tag)::value && KC == 64;
+      constexpr int kStageTaps = kHalo ? 9 : 3;   // taps served by one activation stage
+      constexpr int kSrcStages = kHalo ? 1 : 3;   // activation stages per chunk
+      const int nab = nkb / kStageTaps;           // activation stages per tile
       uint32_t ia = 0, iw = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
@@ -206,13 +228,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         int kb = 0;
-        [[maybe_unused]] int src_i = 0, src_left = src_tab[0] * 3;  // activation stages left in the current source
+        [[maybe_unused]] int src_i = 0, src_left = src_tab[0] * kSrcStages;  // stages left in the current source
         for (int ab = 0; ab < nab; ++ab) {
           [[maybe_unused]] int ksteps = KC / 16;
           if constexpr (kPartial) {
             while (src_left == 0) {
               ++src_i;
-              src_left = src_tab[2 * src_i] * 3;
+              src_left = src_tab[2 * src_i] * kSrcStages;
             }
             --src_left;
             ksteps = src_tab[2 * kMaxSrc + src_i];
@@ -221,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
           mbar_wait(tail + 8u * st, (ia / NA) & 1u);
           tc_fence_after();
           const uint32_t sa = a_base + st * kAStage;
-          for (int dy = 0; dy < 3; ++dy, ++kb) {
+          for (int t = 0; t < kStageTaps; ++t, ++kb) {
             uint32_t sw;
             int ws = 0;
             if (resident) {
@@ -233,7 +255,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
               sw = w_base + ws * kWTap;
             }
             if (elect_one()) {
-              const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
+              uint64_t a_hi, a_lo;
+              if constexpr (kHalo) {
+                const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * 128u;
+                a_hi = make_desc_sbo(sa + off, kHaloW * 128);
+                a_lo = make_desc_sbo(sa + kHaloPlane + off, kHaloW * 128);
+              } else {
+                a_hi = make_desc_kc<KC>(sa + t * kRowStep);
+                a_lo = make_desc_kc<KC>(sa + kAPlane + t * kRowStep);
+              }
               const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWTap / 2);
               const uint32_t first = (kb == 0) ? 0u : 1u;
   #pragma unroll
@@ -252,8 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
                 }
               }
               if (!resident) umma_commit(tail + 8u * (3 * kMaxRing + ws));
-              if (dy == 2) umma_commit(tail + 8u * (kMaxRing + st));
-              if (dy == 2 && ab == nab - 1) umma_commit(tail + 8u * (4 * kMaxRing + acc));
+              if (t == kStageTaps - 1) umma_commit(tail + 8u * (kMaxRing + st));
+              if (t == kStageTaps - 1 && ab == nab - 1) umma_commit(tail + 8u * (4 * kMaxRing + acc));
             }
             __syncwarp();
             if (!resident) ++iw;
@@ -262,8 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         }
       }
     };
-    if (any_partial) run_items(std::true_type{});
-    else run_items(std::false_type{});
+    if (halo) {
+      if (any_partial) run_items(std::true_type{}, std::true_type{});
+      else run_items(std::false_type{}, std::true_type{});
+    } else {
+      if (any_partial) run_items(std::true_type{}, std::false_type{});
+      else run_items(std::false_type{}, std::false_type{});
+    }
   } else {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -346,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
 int smem_bytes_for(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
   const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk) : h.v2_nw * w_tap_bytes(bn, h.kchunk);
-  return h.v2_na * a_stage_bytes(h.kchunk, h.tile_h, h.tile_w) + w + kFixedBytes;
+  return h.v2_na * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo) + w + kFixedBytes;
 }
 
 }  // namespace
@@ -378,15 +413,22 @@ void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int nkb = h.ktot / h.kchunk;
   const int wtap = w_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
-  const int kAStage = a_stage_bytes(h.kchunk, h.tile_h, h.tile_w);
+  const bool can_resident = h.cout <= bn;
+  // wide halo: 16x8 tiles and 64-channel chunks only; resident weights win when both do not fit
+  if (h.halo && (h.kchunk != 64 || h.tile_h != 16 || h.tile_w != 8 ||
+                 (can_resident && w_all + 2 * a_stage_bytes(h.kchunk, h.tile_h, h.tile_w) + kFixedBytes <= kSmemLimit &&
+                  w_all + 2 * kHaloStage + kFixedBytes > kSmemLimit)))
+    h.halo = 0;
+  const int kAStage = a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo);
   h.v2_resident = 0;
-  if (h.cout <= bn && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
+  if (can_resident && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;
     int na = (kSmemLimit - kFixedBytes - w_all) / kAStage;
-    h.v2_na = na > 6 ? 6 : na;
+    const int na_max = h.halo ? 3 : 6;
+    h.v2_na = na > na_max ? na_max : na;
     h.v2_nw = 1;
   } else {
-    h.v2_na = bn >= 128 ? 2 : 3;
+    h.v2_na = h.halo ? 2 : (bn >= 128 ? 2 : 3);
     int nw = (kSmemLimit - kFixedBytes - h.v2_na * kAStage) / wtap;
     h.v2_nw = nw > kMaxRing ? kMaxRing : nw;
   }

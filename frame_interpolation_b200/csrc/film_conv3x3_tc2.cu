@@ -43,6 +43,12 @@ constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
 
 __host__ __device__ constexpr int a_stage_bytes2(int kc) { return 2 * (kTileH + 2) * kTileW * kc * 2; }
+// Wide-halo mode (64-channel chunks): one box (64 ch, 10 px, 18 rows) per plane and chunk serves all nine taps.
+constexpr int kHaloW = kTileW + 2;
+constexpr int kHaloBox = (kTileH + 2) * kHaloW * 64 * 2;        // 23,040 bytes written per plane
+constexpr int kHaloPlane = (kHaloBox + 1023) & ~1023;           // planes start on a swizzle-atom boundary
+constexpr int kHaloStage = 2 * kHaloPlane;                      // 46 KiB vs 3 x 36 KiB for the dx-shifted boxes
+__host__ __device__ constexpr int a_stage_bytes2h(int kc, int halo) { return halo ? kHaloStage : a_stage_bytes2(kc); }
 // bytes of one weight tap per CTA: unfused = half of W_hi + half of W_lo; fused (BN <= 64) = one full
 // plane (W_hi in the leader, W_lo in the peer) + this CTA's half of W_hi
 __host__ __device__ constexpr bool pair_fused(int bn) { return bn <= 64; }
@@ -69,6 +75,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   const int NA = prob->v2_na, NW = prob->v2_nw;
   const bool resident = prob->v2_resident != 0;
+  const bool halo = KC == 64 && prob->halo != 0;
+  const int a_stage = halo ? kHaloStage : kAStage;
   const int nsrc = prob->nsrc;
   const int tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
   const int pairs_y = (tiles_y + 1) / 2;
@@ -84,10 +92,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - raw);
   const uint32_t a_base = base;
-  const uint32_t w_base = a_base + (uint32_t)NA * kAStage;
+  const uint32_t w_base = a_base + (uint32_t)NA * a_stage;
   const uint32_t w_bytes = resident ? (uint32_t)nkb * kWTap : (uint32_t)NW * kWTap;
   const uint32_t tail = w_base + w_bytes;
-  const uint32_t tail_off = (uint32_t)NA * kAStage + w_bytes;
+  const uint32_t tail_off = (uint32_t)NA * a_stage + w_bytes;
   // barrier k at tail + 8k: a_full[0..7], a_empty[8..15], w_full[16..23], w_empty[24..31], t_full[32,33], t_empty[34,35]
   auto a_full = [&](int s) { return tail + 8u * s; };
   auto a_empty = [&](int s) { return tail + 8u * (kMaxRing + s); };
@@ -162,20 +170,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
         const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
         for (int ch = 0; ch < nchunk; ++ch) {
-          for (int dx = 0; dx < 3; ++dx) {
+          // activation stages of this chunk: one wide halo box, or three dx-shifted boxes
+          const int nst = halo ? 1 : 3;
+          for (int dx = 0; dx < nst; ++dx) {
             const int st = ia % NA;
             mbar_wait(a_empty(st), ((ia / NA) & 1u) ^ 1u);
             if (elect_one()) {
-              const uint32_t sa = a_base + st * kAStage;
+              const uint32_t sa = a_base + st * a_stage;
               const uint32_t bar = map_to_cta(a_full(st), 0);
-              if (leader) mbar_expect_tx(a_full(st), 2u * kAStage);
-              tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
-              tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              if (halo) {
+                if (leader) mbar_expect_tx(a_full(st), 4u * kHaloBox);   // two planes x two CTAs
+                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
+                tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
+              } else {
+                if (leader) mbar_expect_tx(a_full(st), 2u * kAStage);
+                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+                tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              }
             }
             __syncwarp();
             ++ia;
             if (!resident) {
-              for (int dy = 0; dy < 3; ++dy, ++kb) {
+              const int ntap = halo ? 9 : 3;   // weight taps consumed against this activation stage
+              for (int t = 0; t < ntap; ++t, ++kb) {
                 const int ws = iw % NW;
                 mbar_wait(w_empty(ws), ((iw / NW) & 1u) ^ 1u);
                 if (elect_one()) {
@@ -207,12 +224,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         mbar_wait(w_full(0), 0);
         tc_fence_after();
       }
-      const int nab = nkb / 3;
-      // two instantiations of the item loop: see film_conv3x3_tc.cu (partial sources skip zero k-steps)
+      // The item loop is instantiated per (partial sources, wide halo): see film_conv3x3_tc.cu.  Halo mode:
+      // one activation stage per chunk carries all nine taps; tap t = 3*dx + dy (the K order of the packed
+      // weights) reads the box at pixel offset (dy, dx), i.e. byte offset (dy * 10 + dx) * 128, with 8-row
+      // groups (one tile row each) 1280 B apart.
       bool any_partial = false;
       for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
-      auto run_items = [&](auto partial_tag) {
+      auto run_items = [&](auto partial_tag, auto halo_tag) {
         constexpr bool kPartial = decltype(partial_tag)::value;
+        constexpr bool kHalo = decltype(halo_tag)::value && KC == 64;
+        constexpr int kStageTaps = kHalo ? 9 : 3;       // taps served by one activation stage
+        constexpr int kSrcStages = kHalo ? 1 : 3;       // activation stages per chunk
+        constexpr int kStageBytes = kHalo ? kHaloStage : kAStage;
+        constexpr int kLoPlane = kHalo ? kHaloPlane : kAPlane;
+        const int nab = nkb / kStageTaps;
         uint32_t ia = 0, iw = 0, it = 0;
         for (int item = item0; item < nitems; item += item_step, ++it) {
           const uint32_t acc = it & 1u;
@@ -220,13 +245,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
           int kb = 0;
-          [[maybe_unused]] int src_i = 0, src_left = src_tab[0] * 3;  // activation stages left in the current source
+          [[maybe_unused]] int src_i = 0, src_left = src_tab[0] * kSrcStages;  // stages left in the current source
           for (int ab = 0; ab < nab; ++ab) {
             [[maybe_unused]] int ksteps = KC / 16;
             if constexpr (kPartial) {  // all-zero tail k-steps are skipped (exact)
               while (src_left == 0) {
                 ++src_i;
-                src_left = src_tab[2 * src_i] * 3;
+                src_left = src_tab[2 * src_i] * kSrcStages;
               }
               --src_left;
               ksteps = src_tab[2 * kMaxSrc + src_i];
@@ -234,8 +259,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const int st = ia % NA;
             mbar_wait(a_full(st), (ia / NA) & 1u);
             tc_fence_after();
-            const uint32_t sa = a_base + st * kAStage;
-            for (int dy = 0; dy < 3; ++dy, ++kb) {
+            const uint32_t sa = a_base + st * kStageBytes;
+            for (int t = 0; t < kStageTaps; ++t, ++kb) {
               uint32_t sw;
               int ws = 0;
               if (resident) {
@@ -247,12 +272,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 sw = w_base + ws * kWTap;
               }
               if (elect_one()) {
-                const uint64_t a_hi = make_desc_kc<KC>(sa + dy * kRowStep), a_lo = make_desc_kc<KC>(sa + kAPlane + dy * kRowStep);
+                uint64_t a_hi, a_lo;
+                if constexpr (kHalo) {
+                  const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * 128u;
+                  a_hi = make_desc_sbo(sa + off, kHaloW * 128);
+                  a_lo = make_desc_sbo(sa + kLoPlane + off, kHaloW * 128);
+                } else {
+                  a_hi = make_desc_kc<KC>(sa + t * kRowStep);
+                  a_lo = make_desc_kc<KC>(sa + kLoPlane + t * kRowStep);
+                }
                 const uint32_t first = (kb == 0) ? 0u : 1u;
                 if constexpr (kFused) {
                   // region X (leader: W_hi, peer: W_lo) is the 2*BN-row operand; region Y = halves of W_hi
                   const uint64_t w_x = make_desc_kc<KC>(sw), w_y = make_desc_kc<KC>(sw + kWFull);
-  #pragma unroll
+#pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
                     if constexpr (kPartial) {
                       if (k >= ksteps) break;
@@ -263,7 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   }
                 } else {
                   const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWHalf);
-  #pragma unroll
+#pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
                     if constexpr (kPartial) {
                       if (k >= ksteps) break;
@@ -275,8 +308,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   }
                 }
                 if (!resident) umma_commit_2sm_mc(w_empty(ws));
-                if (dy == 2) umma_commit_2sm_mc(a_empty(st));
-                if (dy == 2 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+                if (t == kStageTaps - 1) umma_commit_2sm_mc(a_empty(st));
+                if (t == kStageTaps - 1 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
               }
               __syncwarp();
               if (!resident) ++iw;
@@ -285,8 +318,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       };
-      if (any_partial) run_items(std::true_type{});
-      else run_items(std::false_type{});
+      if (halo) {
+        if (any_partial) run_items(std::true_type{}, std::true_type{});
+        else run_items(std::false_type{}, std::true_type{});
+      } else {
+        if (any_partial) run_items(std::true_type{}, std::false_type{});
+        else run_items(std::false_type{}, std::false_type{});
+      }
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================
@@ -369,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 int smem_bytes_for2(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
   const int w = h.v2_resident ? nkb * w_half_tap_bytes(bn, h.kchunk) : h.v2_nw * w_half_tap_bytes(bn, h.kchunk);
-  return h.v2_na * a_stage_bytes2(h.kchunk) + w + kFixedBytes;
+  return h.v2_na * a_stage_bytes2h(h.kchunk, h.halo) + w + kFixedBytes;
 }
 
 }  // namespace
@@ -384,15 +422,21 @@ bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
   const int nkb = h.ktot / h.kchunk;
   const int wtap = w_half_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
-  const int a_stage = a_stage_bytes2(h.kchunk);
+  const bool can_resident = h.cout <= bn && 2 * (long)nkb * wtap < (1 << 20);
+  // wide halo: 64-channel chunks only; resident weights win over the halo when both do not fit
+  if (h.halo && (h.kchunk != 64 || (can_resident && w_all + 2 * a_stage_bytes2(h.kchunk) + kFixedBytes <= kSmemLimit &&
+                                    w_all + 2 * kHaloStage + kFixedBytes > kSmemLimit)))
+    h.halo = 0;
+  const int a_stage = a_stage_bytes2h(h.kchunk, h.halo);
   h.v2_resident = 0;
-  if (h.cout <= bn && 2 * (long)nkb * wtap < (1 << 20) && w_all + 2 * a_stage + kFixedBytes <= kSmemLimit) {
+  if (can_resident && w_all + 2 * a_stage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;
     int na = (kSmemLimit - kFixedBytes - w_all) / a_stage;
-    h.v2_na = na > 6 ? 6 : na;
+    const int na_max = h.halo ? 3 : 6;
+    h.v2_na = na > na_max ? na_max : na;
     h.v2_nw = 1;
   } else {
-    h.v2_na = 3;
+    h.v2_na = h.halo ? 2 : 3;   // a halo stage feeds nine taps: two stages look further ahead than three did
     int nw = (kSmemLimit - kFixedBytes - h.v2_na * a_stage) / wtap;
     h.v2_nw = nw > kMaxRing ? kMaxRing : nw;
     if (h.v2_nw < 2) return false;

@@ -430,6 +430,7 @@ struct Plan {
   int h, w, H, W, off_y, off_x;
   int conv_impl;
   int conv3x3_v2 = 1, num_sms = 148, conv3x3_2cta = 0;
+  int conv3x3_halo = 0;  // 1: pair kernel, 2: pair and single-CTA persistent kernels (wide halo boxes)
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -608,6 +609,8 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.group = 1;
   cp.pair = 0;
   bool pair = false;
+  const int halo_ok = (v2 && kc == kChunk && cp.tile_h == 16 && cp.tile_w == 8) ? P.conv3x3_halo : 0;
+  cp.halo = halo_ok >= 2;
   if (v2) conv3x3_tc_plan(cp, P.num_sms);
   // the pair kernel pays off where weights are re-streamed per tile (halved weight bytes per CTA);
   // layers whose weights stay resident in one CTA's smem are faster on the single-CTA fused kernel
@@ -615,9 +618,17 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   // 18-K-block 128->32 flow conv gains 28 %)
   if (want_pair && (!cp.v2_resident || cp.ktot / cp.kchunk >= 18 || P.conv3x3_2cta >= 2)) {
     ConvProblem alt = cp;
+    alt.halo = halo_ok >= 1;
     if (conv3x3_tc2_plan(alt, P.num_sms)) {
       cp = alt;
       pair = true;
+    }
+  }
+  if (cp.halo) {  // the chosen kernel loads (tile_w + 2)-pixel-wide halo boxes
+    for (int s = 0; s < cp.nsrc; ++s) {
+      const SplitBuf* b = sources[s].buf;
+      make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w + 2, kc);
+      make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w + 2, kc);
     }
   }
   const size_t idx = P.h_probs.size();
@@ -641,7 +652,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
 }
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
-                                        int conv3x3_v2, int num_sms, int conv3x3_2cta) {
+                                        int conv3x3_v2, int num_sms, int conv3x3_2cta, int conv3x3_halo) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
   P.h = h;
@@ -649,6 +660,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.conv_impl = conv_impl;
   P.conv3x3_v2 = conv3x3_v2;
   P.conv3x3_2cta = conv3x3_2cta;
+  P.conv3x3_halo = conv3x3_halo;
   P.num_sms = num_sms;
   // eval/interpolator.py:30-63
   int ph = 0, pw = 0;
@@ -992,6 +1004,7 @@ struct film_handle {
   int use_lanes = 0;   // stream lanes measured no gain at 1080p (smem-saturating kernels cannot co-reside)
   int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
   int conv3x3_2cta = 1;  // CTA-pair (cta_group::2) kernel for streamed-weight 3x3 convs on the large levels
+  int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
@@ -1038,12 +1051,12 @@ static void enqueue_plan(film_handle* h, Plan* P, cudaStream_t origin) {
 
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
-  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta);
+  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2,
-                                       h->num_sms, h->conv3x3_2cta);
+                                       h->num_sms, h->conv3x3_2cta, h->conv3x3_halo);
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1125,6 +1138,7 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     FILM_CUDA(conv3x3_tc_configure());
     FILM_CUDA(conv3x3_tc2_configure());
     if (const char* e2 = getenv("FILM_2CTA")) h->conv3x3_2cta = atoi(e2);
+    if (const char* e3 = getenv("FILM_HALO")) h->conv3x3_halo = atoi(e3);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
     h->model.reset(new Model);
@@ -1174,6 +1188,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "use_lanes") h->use_lanes = value;
   else if (n == "conv3x3_v2") h->conv3x3_v2 = value;
   else if (n == "conv3x3_2cta") h->conv3x3_2cta = value;
+  else if (n == "conv3x3_halo") h->conv3x3_halo = value;
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;

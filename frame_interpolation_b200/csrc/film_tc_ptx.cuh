@@ -92,6 +92,20 @@ __device__ __forceinline__ uint64_t make_desc_kc(uint32_t saddr) {
   return d;
 }
 
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups.  The hardware applies the
+// swizzle XOR on ABSOLUTE smem address bits (7..9 -> 4..6) and base_offset stays 0: measured on B200 with
+// tools/ubench/desc_offset_test.cu -- the start address may sit at any 128-byte row inside the 1024-byte
+// atom and SBO need not be a multiple of 1024 (rows of a 10-pixel-wide halo box: SBO = 1280).
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format=F32 [4,6),
 // a_format [7,10), b_format [10,13) (0 = F16, 1 = BF16), K-major A and B, N>>3 [17,23), M>>4 [24,29).
 template <int BN>

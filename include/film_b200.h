@@ -128,6 +128,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "conv3x3_v2"  : 1 = persistent tap-reuse kernel for 3x3 convs (default), 0 = generic kernel
  *   "conv3x3_2cta": 1 = CTA-pair (tcgen05 cta_group::2, M = 256) kernel for the streamed-weight 3x3
  *                   convs of the large pyramid levels (default), 0 = off, 2 = every eligible layer
+ *   "conv3x3_halo": wide halo boxes -- one (64 ch, 10 px, 18 rows) TMA box per chunk serves all nine taps
+ *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
+ *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0) */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
 

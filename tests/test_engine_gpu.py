@@ -258,9 +258,11 @@ def test_cli_end_to_end(tmp_path, synthetic_weights):
     np.testing.assert_array_equal(mid, eval_util.read_image(str(tmp_path / "mid.png")))
 
 
-@pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0)])
+@pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0),
+                                          ("conv3x3_halo", 0), ("conv3x3_halo", 1)])
 def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
-    """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers) meets the same bar."""
+    """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers, wide-halo boxes off /
+    pair-only; the default is wide halo in both persistent kernels) meets the same bar."""
     from frame_interpolation_b200.interpolator import Interpolator
     x0, x1 = synthetic.frame_pair(256, 320, seed=13, n_waves=8)
     ref = oracle(x0, x1, DT)

@@ -17,10 +17,12 @@
 #include "../../frame_interpolation_b200/csrc/film_tc_ptx.cuh"
 using namespace film::tc;
 
-constexpr int kRows = 18, kN = 64, kC = 64;
+constexpr int kRows = 18, kN = 64;
+// kc = 64: 128-byte rows, SWIZZLE_128B (chunk ^= address bits 7..9); kc = 32: 64-byte rows, SWIZZLE_64B
+// (chunk ^= address bits 7..8)
 
 __global__ void __launch_bounds__(128, 1)
-k_test(const __nv_bfloat16* img, const __nv_bfloat16* wgt, int pitch_px, int dy, int dx, int variant, float* out) {
+k_test(const __nv_bfloat16* img, const __nv_bfloat16* wgt, int kC, int pitch_px, int dy, int dx, int variant, float* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -29,17 +31,18 @@ k_test(const __nv_bfloat16* img, const __nv_bfloat16* wgt, int pitch_px, int dy,
   __shared__ uint32_t tmem_ptr;
   const uint32_t a_off = 0, b_off = 32 * 1024;
   // image: pixel p (row-major, pitch_px wide) at byte offset p*128, 16-byte chunks XOR-swizzled on address bits 7..9
-  for (int i = threadIdx.x; i < kRows * pitch_px * 8; i += blockDim.x) {
-    const int p = i / 8, j = i % 8;
-    const uint32_t addr = base + a_off + p * 128;
-    const int js = j ^ ((addr >> 7) & 7);
-    *reinterpret_cast<uint4*>(sm + a_off + p * 128 + js * 16) = *reinterpret_cast<const uint4*>(img + (size_t)p * kC + j * 8);
+  const int rb = kC * 2, nch = rb / 16, xmask = nch - 1;   // row bytes, 16-byte chunks per row
+  for (int i = threadIdx.x; i < kRows * pitch_px * nch; i += blockDim.x) {
+    const int p = i / nch, j = i % nch;
+    const uint32_t addr = base + a_off + p * rb;
+    const int js = j ^ ((addr >> 7) & xmask);
+    *reinterpret_cast<uint4*>(sm + a_off + p * rb + js * 16) = *reinterpret_cast<const uint4*>(img + (size_t)p * kC + j * 8);
   }
-  for (int i = threadIdx.x; i < kN * 8; i += blockDim.x) {
-    const int n = i / 8, j = i % 8;
-    const uint32_t addr = base + b_off + n * 128;
-    const int js = j ^ ((addr >> 7) & 7);
-    *reinterpret_cast<uint4*>(sm + b_off + n * 128 + js * 16) = *reinterpret_cast<const uint4*>(wgt + (size_t)n * kC + j * 8);
+  for (int i = threadIdx.x; i < kN * nch; i += blockDim.x) {
+    const int n = i / nch, j = i % nch;
+    const uint32_t addr = base + b_off + n * rb;
+    const int js = j ^ ((addr >> 7) & xmask);
+    *reinterpret_cast<uint4*>(sm + b_off + n * rb + js * 16) = *reinterpret_cast<const uint4*>(wgt + (size_t)n * kC + j * 8);
   }
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -53,17 +56,23 @@ k_test(const __nv_bfloat16* img, const __nv_bfloat16* wgt, int pitch_px, int dy,
   const uint32_t tm = tmem_ptr;
   if (threadIdx.x == 0) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a_start = base + a_off + (dy * pitch_px + dx) * 128;
-    for (int k = 0; k < 4; ++k) {
+    const uint32_t a_start = base + a_off + (dy * pitch_px + dx) * rb;
+    const uint64_t type = kC == 64 ? 2 : 4;
+    for (int k = 0; k < kC / 16; ++k) {
       const uint32_t sa = a_start + k * 32;
       uint64_t ad = 0;
       ad |= (uint64_t)((sa & 0x3FFFFu) >> 4);
       ad |= (uint64_t)1 << 16;
-      ad |= (uint64_t)((pitch_px * 128) >> 4) << 32;  // SBO: next 8-row group = next image row
+      ad |= (uint64_t)((pitch_px * rb) >> 4) << 32;  // SBO: next 8-row group = next image row
       ad |= (uint64_t)1 << 46;
       if (variant == 1) ad |= (uint64_t)((a_start >> 7) & 7) << 49;
-      ad |= (uint64_t)2 << 61;
-      const uint64_t bd = make_desc(base + b_off + k * 32);
+      ad |= type << 61;
+      uint64_t bd = 0;
+      bd |= (uint64_t)(((base + b_off + k * 32) & 0x3FFFFu) >> 4);
+      bd |= (uint64_t)1 << 16;
+      bd |= (uint64_t)((8 * rb) >> 4) << 32;
+      bd |= (uint64_t)1 << 46;
+      bd |= type << 61;
       umma(tm, ad, bd, idesc, k > 0 ? 1u : 0u);
     }
     umma_commit(smem_u32(&bar));
@@ -85,7 +94,8 @@ k_test(const __nv_bfloat16* img, const __nv_bfloat16* wgt, int pitch_px, int dy,
 
 int main() {
   const int max_pitch = 16;
-  std::vector<__nv_bfloat16> h_img((size_t)kRows * max_pitch * kC), h_w((size_t)kN * kC);
+  const int kCmax = 64;
+  std::vector<__nv_bfloat16> h_img((size_t)kRows * max_pitch * kCmax), h_w((size_t)kN * kCmax);
   std::vector<float> f_img(h_img.size()), f_w(h_w.size());
   srand(7);
   for (size_t i = 0; i < h_img.size(); ++i) { f_img[i] = (float)(rand() % 15 - 7); h_img[i] = __float2bfloat16(f_img[i]); }
@@ -98,15 +108,17 @@ int main() {
   cudaMemcpy(d_img, h_img.data(), h_img.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(k_test, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  struct Case { int pitch, dy, dx; } cases[] = {{8, 0, 0}, {8, 2, 0}, {10, 0, 0}, {10, 0, 1}, {10, 0, 2}, {10, 1, 1},
-                                                {10, 2, 2}, {16, 1, 3}, {9, 1, 1}};
+  struct Case { int kc, pitch, dy, dx; } cases[] = {{64, 8, 0, 0}, {64, 8, 2, 0}, {64, 10, 0, 0}, {64, 10, 0, 1}, {64, 10, 0, 2},
+                                                    {64, 10, 1, 1}, {64, 10, 2, 2}, {64, 9, 1, 1},
+                                                    {32, 8, 0, 0}, {32, 8, 2, 0}, {32, 10, 0, 0}, {32, 10, 0, 1}, {32, 10, 0, 2},
+                                                    {32, 10, 1, 1}, {32, 10, 2, 2}, {32, 9, 1, 1}};
   std::vector<float> h_out(128 * kN);
   for (auto& c : cases) {
     for (int variant = 0; variant < 2; ++variant) {
       cudaMemset(d_out, 0, 128 * kN * 4);
-      k_test<<<1, 128, 64 * 1024>>>(d_img, d_w, c.pitch, c.dy, c.dx, variant, d_out);
+      k_test<<<1, 128, 64 * 1024>>>(d_img, d_w, c.kc, c.pitch, c.dy, c.dx, variant, d_out);
       cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("pitch %d dy %d dx %d variant %d: %s\n", c.pitch, c.dy, c.dx, variant, cudaGetErrorString(e)); return 1; }
+      if (e != cudaSuccess) { printf("kc %d pitch %d dy %d dx %d variant %d: %s\n", c.kc, c.pitch, c.dy, c.dx, variant, cudaGetErrorString(e)); return 1; }
       cudaMemcpy(h_out.data(), d_out, 128 * kN * 4, cudaMemcpyDeviceToHost);
       double max_err = 0;
       int bad = 0;
@@ -114,13 +126,13 @@ int main() {
         const int p = (r / 8 + c.dy) * c.pitch + (r % 8) + c.dx;
         for (int n = 0; n < kN; ++n) {
           double acc = 0;
-          for (int k = 0; k < kC; ++k) acc += (double)f_img[(size_t)p * kC + k] * f_w[(size_t)n * kC + k];
+          for (int k = 0; k < c.kc; ++k) acc += (double)f_img[(size_t)p * c.kc + k] * f_w[(size_t)n * c.kc + k];
           const double err = fabs(acc - h_out[(size_t)r * kN + n]);
           if (err > max_err) max_err = err;
           if (err != 0) ++bad;
         }
       }
-      printf("pitch %2d px  tap (dy %d, dx %d)  base_offset %s : max |err| %.1f, %d / %d wrong  %s\n", c.pitch, c.dy, c.dx,
+      printf("kc %d  pitch %2d px  tap (dy %d, dx %d)  base_offset %s : max |err| %.1f, %d / %d wrong  %s\n", c.kc, c.pitch, c.dy, c.dx,
              variant ? "(addr>>7)&7" : "0          ", max_err, bad, 128 * kN, bad ? "MISMATCH" : "exact");
     }
   }
