@@ -1049,14 +1049,34 @@ static void enqueue_plan(film_handle* h, Plan* P, cudaStream_t origin) {
   if (P->tok_end >= 0) FILM_CUDA(cudaStreamWaitEvent(origin, h->token_events[P->tok_end], 0));
 }
 
+// Frees every cached plan (graphs + activation arenas) once the handle's stream has drained.
+static void drop_plans(film_handle* h) {
+  cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
+  (void)cudaGetLastError();
+  h->last_plan = nullptr;
+  h->dev_events_valid = false;
+  h->plans.clear();
+}
+
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
            h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
-  std::unique_ptr<Plan> p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2,
-                                       h->num_sms, h->conv3x3_2cta, h->conv3x3_halo);
+  std::unique_ptr<Plan> p;
+  try {
+    p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
+                   h->conv3x3_2cta, h->conv3x3_halo);
+  } catch (const Error&) {
+    // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
+    // them, drop the cache and retry once before giving up.
+    if (h->plans.empty()) throw;
+    drop_plans(h);
+    p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
+                   h->conv3x3_2cta, h->conv3x3_halo);
+  }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
     FILM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1189,6 +1209,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "conv3x3_v2") h->conv3x3_v2 = value;
   else if (n == "conv3x3_2cta") h->conv3x3_2cta = value;
   else if (n == "conv3x3_halo") h->conv3x3_halo = value;
+  else if (n == "clear_plans") drop_plans(h);
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;

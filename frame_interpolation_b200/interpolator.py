@@ -218,6 +218,11 @@ class Interpolator:
     def set_option(self, name: str, value: int) -> None:
         self._check(self._lib.film_set_option(self._handle, name.encode(), int(value)))
 
+    def clear_cache(self) -> None:
+        """Drops every cached per-shape plan (CUDA graph + activation arena) of this engine; the next call of a
+        shape rebuilds it. For services that see many resolutions: plans are never evicted otherwise."""
+        self.set_option("clear_plans", 1)
+
     def profile(self) -> dict:
         p = _lib.FilmProfile()
         self._check(self._lib.film_profile(self._handle, C.byref(p)))

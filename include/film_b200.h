@@ -131,7 +131,11 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "conv3x3_halo": wide halo boxes -- one (64 ch, 10 px, 18 rows) TMA box per chunk serves all nine taps
  *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
  *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
- *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0) */
+ *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)
+ *   "clear_plans" : (any value) drop every cached (H, W, align) plan -- CUDA graph and activation arena --
+ *                   after draining the handle's stream.  Plans are cached per shape and never evicted
+ *                   otherwise, except that a shape whose arena cannot be allocated triggers one
+ *                   drop-and-retry before FILM_ERR_CUDA is returned. */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
 
 /* Debug/parity hook: copies an intermediate tensor of the LAST call to host as float32

@@ -297,3 +297,18 @@ def test_results_live_in_distinct_pinned_buffers(engine):
     gc.collect()
     for _ in range(8):                           # steady state: buffers are recycled, results stay right
         np.testing.assert_array_equal(engine(a0, a1, DT), keep)
+
+
+def test_clear_cache_drops_plans_and_results_are_reproduced(synthetic_weights):
+    """Plans (CUDA graph + activation arena) are cached per shape; clear_cache() frees them and the next call
+    rebuilds the plan with identical results."""
+    from frame_interpolation_b200.interpolator import Interpolator
+    eng = Interpolator(synthetic_weights[0], align=64)
+    x0, x1 = synthetic.frame_pair(128, 192, seed=21, n_waves=8)
+    y0, y1 = synthetic.frame_pair(64, 64, seed=22, n_waves=8)
+    a, b = eng(x0, x1, DT).copy(), eng(y0, y1, DT).copy()
+    assert eng.profile()["arena_bytes"] > 0
+    eng.clear_cache()
+    np.testing.assert_array_equal(eng(y0, y1, DT), b)
+    np.testing.assert_array_equal(eng(x0, x1, DT), a)
+    eng.close()
