@@ -46,11 +46,11 @@ __host__ __device__ constexpr int a_stage_bytes(int kc, int th, int tw) { return
 // 1280 B between 8-row groups (hardware check: tools/ubench/desc_offset_test.cu).  2.4x less L2 -> smem
 // activation traffic than the three dx-shifted boxes.
 constexpr int kHaloW = 10, kHaloRows = 18;
-constexpr int kHaloBox = kHaloRows * kHaloW * 64 * 2;           // 23,040 bytes written per plane
-constexpr int kHaloPlane = (kHaloBox + 1023) & ~1023;           // planes start on a swizzle-atom boundary
-constexpr int kHaloStage = 2 * kHaloPlane;
+__host__ __device__ constexpr int halo_box_bytes(int kc) { return kHaloRows * kHaloW * kc * 2; }  // 23,040 for KC = 64
+__host__ __device__ constexpr int halo_plane_bytes(int kc) { return (halo_box_bytes(kc) + 1023) & ~1023; }  // 1 KiB-aligned planes
+__host__ __device__ constexpr int halo_stage_bytes(int kc) { return 2 * halo_plane_bytes(kc); }
 __host__ __device__ constexpr int a_stage_bytes_h(int kc, int th, int tw, int halo) {
-  return halo ? kHaloStage : a_stage_bytes(kc, th, tw);
+  return halo ? halo_stage_bytes(kc) : a_stage_bytes(kc, th, tw);
 }
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
   extern __shared__ uint8_t smem_raw[];
   constexpr int kWTap = BN * KC * 2 * 2;
   const int kTileH = prob->tile_h, kTileW = prob->tile_w;
-  const bool halo = KC == 64 && prob->halo != 0;   // plan guarantees 16x8 tiles
+  constexpr int kHaloBox = halo_box_bytes(KC), kHaloPlane = halo_plane_bytes(KC), kHaloStage = halo_stage_bytes(KC);
+  const bool halo = prob->halo != 0;   // plan guarantees 16x8 tiles
   const int kAPlane = halo ? kHaloPlane : a_plane_bytes(KC, kTileH, kTileW);
   const int kAStage = halo ? kHaloStage : a_stage_bytes(KC, kTileH, kTileW);
   const int kRowStep = kTileW * KC * 2;  // one tile row of pixels = tile_w/8 swizzle atoms
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     // packed weights) reads the box at byte offset (dy * 10 + dx) * 128, 8-row groups 1280 B apart.
     auto run_items = [&](auto partial_tag, auto halo_tag) {
       constexpr bool kPartial = decltype(partial_tag)::value;
-      constexpr bool kHalo = decltype(halo_tag)::value && KC == 64;
+      constexpr bool kHalo = decltype(halo_tag)::value;
       constexpr int kStageTaps = kHalo ? 9 : 3;   // taps served by one activation stage
       constexpr int kSrcStages = kHalo ? 1 : 3;   // activation stages per chunk
       const int nab = nkb / kStageTaps;           // activation stages per tile
@@ -257,9 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             if (elect_one()) {
               uint64_t a_hi, a_lo;
               if constexpr (kHalo) {
-                const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * 128u;
-                a_hi = make_desc_sbo(sa + off, kHaloW * 128);
-                a_lo = make_desc_sbo(sa + kHaloPlane + off, kHaloW * 128);
+                constexpr uint32_t kPx = KC * 2;   // bytes of one pixel row of the box
+                const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * kPx;
+                a_hi = make_desc_sbo<KC>(sa + off, kHaloW * kPx);
+                a_lo = make_desc_sbo<KC>(sa + kHaloPlane + off, kHaloW * kPx);
               } else {
                 a_hi = make_desc_kc<KC>(sa + t * kRowStep);
                 a_lo = make_desc_kc<KC>(sa + kAPlane + t * kRowStep);
@@ -414,10 +416,10 @@ void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int wtap = w_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
   const bool can_resident = h.cout <= bn;
-  // wide halo: 16x8 tiles and 64-channel chunks only; resident weights win when both do not fit
-  if (h.halo && (h.kchunk != 64 || h.tile_h != 16 || h.tile_w != 8 ||
+  // wide halo (the engine allows it per chunk size): 16x8 tiles only; resident weights win when both do not fit
+  if (h.halo && (h.tile_h != 16 || h.tile_w != 8 ||
                  (can_resident && w_all + 2 * a_stage_bytes(h.kchunk, h.tile_h, h.tile_w) + kFixedBytes <= kSmemLimit &&
-                  w_all + 2 * kHaloStage + kFixedBytes > kSmemLimit)))
+                  w_all + 2 * halo_stage_bytes(h.kchunk) + kFixedBytes > kSmemLimit)))
     h.halo = 0;
   const int kAStage = a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo);
   h.v2_resident = 0;

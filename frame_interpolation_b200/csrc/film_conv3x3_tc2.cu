@@ -43,12 +43,12 @@ constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
 
 __host__ __device__ constexpr int a_stage_bytes2(int kc) { return 2 * (kTileH + 2) * kTileW * kc * 2; }
-// Wide-halo mode (64-channel chunks): one box (64 ch, 10 px, 18 rows) per plane and chunk serves all nine taps.
+// Wide-halo mode: one box (KC ch, 10 px, 18 rows) per plane and chunk serves all nine taps.
 constexpr int kHaloW = kTileW + 2;
-constexpr int kHaloBox = (kTileH + 2) * kHaloW * 64 * 2;        // 23,040 bytes written per plane
-constexpr int kHaloPlane = (kHaloBox + 1023) & ~1023;           // planes start on a swizzle-atom boundary
-constexpr int kHaloStage = 2 * kHaloPlane;                      // 46 KiB vs 3 x 36 KiB for the dx-shifted boxes
-__host__ __device__ constexpr int a_stage_bytes2h(int kc, int halo) { return halo ? kHaloStage : a_stage_bytes2(kc); }
+__host__ __device__ constexpr int halo_box_bytes(int kc) { return (kTileH + 2) * kHaloW * kc * 2; }  // 23,040 (KC 64)
+__host__ __device__ constexpr int halo_plane_bytes(int kc) { return (halo_box_bytes(kc) + 1023) & ~1023; }  // 1 KiB-aligned planes
+__host__ __device__ constexpr int halo_stage_bytes(int kc) { return 2 * halo_plane_bytes(kc); }  // 46 KiB vs 3 x 36 KiB
+__host__ __device__ constexpr int a_stage_bytes2h(int kc, int halo) { return halo ? halo_stage_bytes(kc) : a_stage_bytes2(kc); }
 // bytes of one weight tap per CTA: unfused = half of W_hi + half of W_lo; fused (BN <= 64) = one full
 // plane (W_hi in the leader, W_lo in the peer) + this CTA's half of W_hi
 __host__ __device__ constexpr bool pair_fused(int bn) { return bn <= 64; }
@@ -67,6 +67,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   constexpr int kWFull = BN * KC * 2;         // one plane, all rows of the N tile
   constexpr int kWTap = w_half_tap_bytes(BN, KC);
   constexpr int kRowStep = kTileW * KC * 2;
+  constexpr int kHaloBox = halo_box_bytes(KC), kHaloPlane = halo_plane_bytes(KC), kHaloStage = halo_stage_bytes(KC);
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
   constexpr uint32_t kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
 
@@ -75,7 +76,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   const int NA = prob->v2_na, NW = prob->v2_nw;
   const bool resident = prob->v2_resident != 0;
-  const bool halo = KC == 64 && prob->halo != 0;
+  const bool halo = prob->halo != 0;
   const int a_stage = halo ? kHaloStage : kAStage;
   const int nsrc = prob->nsrc;
   const int tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
@@ -232,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
       auto run_items = [&](auto partial_tag, auto halo_tag) {
         constexpr bool kPartial = decltype(partial_tag)::value;
-        constexpr bool kHalo = decltype(halo_tag)::value && KC == 64;
+        constexpr bool kHalo = decltype(halo_tag)::value;
         constexpr int kStageTaps = kHalo ? 9 : 3;       // taps served by one activation stage
         constexpr int kSrcStages = kHalo ? 1 : 3;       // activation stages per chunk
         constexpr int kStageBytes = kHalo ? kHaloStage : kAStage;
@@ -274,9 +275,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               if (elect_one()) {
                 uint64_t a_hi, a_lo;
                 if constexpr (kHalo) {
-                  const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * 128u;
-                  a_hi = make_desc_sbo(sa + off, kHaloW * 128);
-                  a_lo = make_desc_sbo(sa + kLoPlane + off, kHaloW * 128);
+                  constexpr uint32_t kPx = KC * 2;   // bytes of one pixel row of the box
+                  const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * kPx;
+                  a_hi = make_desc_sbo<KC>(sa + off, kHaloW * kPx);
+                  a_lo = make_desc_sbo<KC>(sa + kLoPlane + off, kHaloW * kPx);
                 } else {
                   a_hi = make_desc_kc<KC>(sa + t * kRowStep);
                   a_lo = make_desc_kc<KC>(sa + kLoPlane + t * kRowStep);
@@ -423,9 +425,9 @@ bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
   const int wtap = w_half_tap_bytes(bn, h.kchunk);
   const int w_all = nkb * wtap;
   const bool can_resident = h.cout <= bn && 2 * (long)nkb * wtap < (1 << 20);
-  // wide halo: 64-channel chunks only; resident weights win over the halo when both do not fit
-  if (h.halo && (h.kchunk != 64 || (can_resident && w_all + 2 * a_stage_bytes2(h.kchunk) + kFixedBytes <= kSmemLimit &&
-                                    w_all + 2 * kHaloStage + kFixedBytes > kSmemLimit)))
+  // wide halo (the engine allows it per chunk size): resident weights win when both do not fit
+  if (h.halo && can_resident && w_all + 2 * a_stage_bytes2(h.kchunk) + kFixedBytes <= kSmemLimit &&
+      w_all + 2 * halo_stage_bytes(h.kchunk) + kFixedBytes > kSmemLimit)
     h.halo = 0;
   const int a_stage = a_stage_bytes2h(h.kchunk, h.halo);
   h.v2_resident = 0;

@@ -430,7 +430,7 @@ struct Plan {
   int h, w, H, W, off_y, off_x;
   int conv_impl;
   int conv3x3_v2 = 1, num_sms = 148, conv3x3_2cta = 0;
-  int conv3x3_halo = 0;  // 1: pair kernel, 2: pair and single-CTA persistent kernels (wide halo boxes)
+  int conv3x3_halo = 0;  // 1: pair kernel, 2: + single-CTA persistent kernel, 3: + 32-channel-chunk layers
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -609,7 +609,10 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   cp.group = 1;
   cp.pair = 0;
   bool pair = false;
-  const int halo_ok = (v2 && kc == kChunk && cp.tile_h == 16 && cp.tile_w == 8) ? P.conv3x3_halo : 0;
+  // wide halo level: 1 = pair kernel, 2 = + single-CTA kernel (64-channel chunks), 3 = + 32-channel chunks
+  // (SWIZZLE_64B descriptor offsets verified by tools/ubench/desc_offset_test.cu; kernels not yet timed)
+  int halo_ok = (v2 && cp.tile_h == 16 && cp.tile_w == 8) ? P.conv3x3_halo : 0;
+  if (kc != kChunk && halo_ok < 3) halo_ok = 0;
   cp.halo = halo_ok >= 2;
   if (v2) conv3x3_tc_plan(cp, P.num_sms);
   // the pair kernel pays off where weights are re-streamed per tile (halved weight bytes per CTA);
@@ -1005,6 +1008,7 @@ struct film_handle {
   int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
   int conv3x3_2cta = 1;  // CTA-pair (cta_group::2) kernel for streamed-weight 3x3 convs on the large levels
   int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
+                         // persistent kernels (default), 3 also the 32-channel-chunk layers (experimental)
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;

@@ -92,17 +92,19 @@ __device__ __forceinline__ uint64_t make_desc_kc(uint32_t saddr) {
   return d;
 }
 
-// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups.  The hardware applies the
-// swizzle XOR on ABSOLUTE smem address bits (7..9 -> 4..6) and base_offset stays 0: measured on B200 with
-// tools/ubench/desc_offset_test.cu -- the start address may sit at any 128-byte row inside the 1024-byte
-// atom and SBO need not be a multiple of 1024 (rows of a 10-pixel-wide halo box: SBO = 1280).
+// K-major swizzled descriptor with an explicit stride between 8-row groups.  The hardware applies the
+// swizzle XOR on ABSOLUTE smem address bits (7..9 -> 4..6; 7..8 -> 4..5 for SWIZZLE_64B) and base_offset stays
+// 0: measured on B200 with tools/ubench/desc_offset_test.cu -- the start address may sit at any row inside
+// the swizzle atom and SBO need not be a multiple of the atom (rows of a 10-pixel-wide halo box: SBO = 10 rows).
+template <int KC>
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  constexpr uint64_t kType = (KC == 64) ? 2 : 4;   // SWIZZLE_128B (128-byte rows) / SWIZZLE_64B (64-byte rows)
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= kType << 61;
   return d;
 }
 

@@ -130,7 +130,8 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   convs of the large pyramid levels (default), 0 = off, 2 = every eligible layer
  *   "conv3x3_halo": wide halo boxes -- one (64 ch, 10 px, 18 rows) TMA box per chunk serves all nine taps
  *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
- *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
+ *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes,
+ *                   3 = also the 32-channel-chunk layers (experimental: not yet validated on hardware)
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)
  *   "clear_plans" : (any value) drop every cached (H, W, align) plan -- CUDA graph and activation arena --
  *                   after draining the handle's stream.  Plans are cached per shape and never evicted
