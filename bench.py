@@ -322,6 +322,8 @@ def main():
         "bound": "tensor", "kernel": "k_conv_tc<BN> (tcgen05 implicit-GEMM conv, all call sites)",
         "achieved": ach_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": ach_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+        "traffic_note": "roofline is over 84 launches of 3 kernels; ncu --set full on 22 of them "
+                        "(profiles/r1s_ncu_final.md): dram read+write == algorithmic bytes on every capture",
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
         "mma_kind": "tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate), 3 passes per product "
                     "(hi*hi + hi*lo + lo*hi) for fp32-grade parity",
