@@ -30,6 +30,11 @@
  *
  * There is no CPU fallback: every entry point fails with status 2 if no sm_100
  * device is present.
+ *
+ * Threading: a handle owns one CUDA stream, its per-shape plans (activation arenas, CUDA
+ * graphs) and its staging buffers, so calls on ONE handle must be serialised by the caller;
+ * different handles (one per GPU, or several per GPU when memory allows: ~20 GB per cached
+ * 1080p shape) are independent and may be driven from different threads or processes.
  */
 #ifndef FILM_B200_H_
 #define FILM_B200_H_
