@@ -16,6 +16,7 @@ EXPORTS = [
     "film_interpolate_device", "film_interpolate_recursive", "film_host_alloc", "film_host_free",
     "film_synchronize", "film_profile", "film_set_option",
     "film_debug_read", "film_op_table", "film_last_error", "film_version",
+    "film_get_option", "film_stage_count", "film_stage_name",
 ]
 
 
@@ -67,6 +68,12 @@ def load() -> C.CDLL:
     lib.film_profile.restype = C.c_int
     lib.film_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.film_set_option.restype = C.c_int
+    lib.film_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+    lib.film_get_option.restype = C.c_int
+    lib.film_stage_count.argtypes = []
+    lib.film_stage_count.restype = C.c_int
+    lib.film_stage_name.argtypes = [C.c_int, C.c_char_p, C.c_int]
+    lib.film_stage_name.restype = C.c_int
     lib.film_debug_read.argtypes = [C.c_void_p, C.c_char_p, fp, C.POINTER(C.c_int64)]
     lib.film_debug_read.restype = C.c_int
     lib.film_op_table.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]

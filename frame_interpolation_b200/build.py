@@ -47,7 +47,10 @@ def _digest(extra: str) -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     flags = list(NVCC_FLAGS)
-    if os.environ.get("FILM_SPLIT", "bf16") == "fp16":
+    # 16-bit split format of activations and weights: fp16 (default: 11-bit planes, which is what makes the
+    # single-pass stages of the precision plan possible) or bf16 (FILM_SPLIT=bf16: 8-bit planes, every stage
+    # must then run three-pass -- set the option onepass_mask = 0)
+    if os.environ.get("FILM_SPLIT", "fp16") == "fp16":
         flags.append("-DFILM_SPLIT_FP16")
     if verbose:
         flags += ["-Xptxas", "-v"]

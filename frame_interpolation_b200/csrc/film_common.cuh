@@ -64,7 +64,14 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
 }
 __device__ __forceinline__ void split_pack2_generic(float a, float b, uint32_t& hi, uint32_t& lo) {
 #else
+// fp16: packed saturating converts (F2FP.SATFINITE.F16.F32.PACK_AB; |x| > 65504 clamps instead of turning into
+// inf), the hi halves come back through HADD2.F32 -> 6 instructions per pair, like the bf16 form
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+}
+__device__ __forceinline__ void split_pack2_generic(float a, float b, uint32_t& hi, uint32_t& lo) {
 #endif
   sp_t ah, al, bh, bl;
   split2(a, ah, al);
@@ -94,8 +101,10 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float* v
     v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
     v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
 #else
-    v[2 * i] = sp_bits_to_float(hw[i] & 0xffffu) + sp_bits_to_float(lw[i] & 0xffffu);
-    v[2 * i + 1] = sp_bits_to_float(hw[i] >> 16) + sp_bits_to_float(lw[i] >> 16);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = hf.x + lf.x;
+    v[2 * i + 1] = hf.y + lf.y;
 #endif
   }
 }
@@ -127,6 +136,44 @@ __device__ __forceinline__ void pack_store16(const float* v, sp_t* hi_dst, sp_t*
   pack8(v + 8, h1, l1);
   st256(hi_dst, h0, h1);
   st256(lo_dst, l0, l1);
+}
+// hi plane only (destinations whose consumers are all single-pass convs)
+__device__ __forceinline__ uint32_t pack2_hi(float a, float b) {
+#ifdef FILM_SPLIT_FP16
+  uint32_t hi;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  return hi;
+#else
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h2);
+#endif
+}
+__device__ __forceinline__ void pack_store16_hi(const float* v, sp_t* hi_dst) {
+  uint4 h0, h1;
+  h0.x = pack2_hi(v[0], v[1]);   h0.y = pack2_hi(v[2], v[3]);   h0.z = pack2_hi(v[4], v[5]);   h0.w = pack2_hi(v[6], v[7]);
+  h1.x = pack2_hi(v[8], v[9]);   h1.y = pack2_hi(v[10], v[11]); h1.z = pack2_hi(v[12], v[13]); h1.w = pack2_hi(v[14], v[15]);
+  st256(hi_dst, h0, h1);
+}
+// unpack 8 / 16 consecutive channels of the hi plane alone (x ~ hi: 11-bit operands of a single-pass conv)
+__device__ __forceinline__ void unpack8_hi(const uint4& h, float* v) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#ifndef FILM_SPLIT_FP16
+    v[2 * i] = __uint_as_float(hw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u);
+#else
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    v[2 * i] = hf.x;
+    v[2 * i + 1] = hf.y;
+#endif
+  }
+}
+__device__ __forceinline__ void load_unpack16_hi(const sp_t* hi_src, float* v) {
+  uint4 h0, h1;
+  ld256_nc(hi_src, h0, h1);
+  unpack8_hi(h0, v);
+  unpack8_hi(h1, v + 8);
 }
 __device__ __forceinline__ void load_unpack16(const sp_t* hi_src, const sp_t* lo_src, float* v) {
   uint4 h0, h1, l0, l1;

@@ -85,6 +85,11 @@ struct alignas(64) ConvProblem {
                           // Set to 1 by the engine to ALLOW it; the plan functions keep or clear it.
   int bn;                 // N tile (32/64/128/256): conv_tc_block_n(cout), or smaller on tiny levels so that
                           // a K-serial problem spreads over more SMs
+  int passes;             // MMAs per product: 3 = A_hi*W_hi + A_hi*W_lo + A_lo*W_hi (fp32-grade), 1 = A_hi*W_hi only
+                          // (11-bit fp16 operands, fp32 accumulate; only the hi planes of the activations and
+                          // weights are loaded).  Chosen per call site by the engine's precision plan
+                          // (film_engine.cu).
+  int out_lo_skip;        // 1: every consumer of the destination reads the hi plane only -> the lo plane is not written
 };
 
 // launchers (film_conv_tc.cu / film_kernels.cu)

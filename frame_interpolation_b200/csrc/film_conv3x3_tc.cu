@@ -49,25 +49,30 @@ constexpr int kHaloW = 10, kHaloRows = 18;
 __host__ __device__ constexpr int halo_box_bytes(int kc) { return kHaloRows * kHaloW * kc * 2; }  // 23,040 for KC = 64
 __host__ __device__ constexpr int halo_plane_bytes(int kc) { return (halo_box_bytes(kc) + 1023) & ~1023; }  // 1 KiB-aligned planes
 __host__ __device__ constexpr int halo_stage_bytes(int kc) { return 2 * halo_plane_bytes(kc); }
-__host__ __device__ constexpr int a_stage_bytes_h(int kc, int th, int tw, int halo) {
-  return halo ? halo_stage_bytes(kc) : a_stage_bytes(kc, th, tw);
+// `planes` = 2 (hi + lo, three-pass product) or 1 (single-pass layers load the hi planes only)
+__host__ __device__ constexpr int a_stage_bytes_h(int kc, int th, int tw, int halo, int planes = 2) {
+  return planes * (halo ? halo_plane_bytes(kc) : a_plane_bytes(kc, th, tw));
 }
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
 
-__host__ __device__ inline int w_tap_bytes(int bn, int kc) { return bn * kc * 2 * 2; }  // [BN x KC] hi + lo
+__host__ __device__ inline int w_tap_bytes(int bn, int kc, int planes = 2) { return bn * kc * 2 * planes; }  // [BN x KC] hi (+ lo)
 
 template <int BN, int KC>
 __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* __restrict__ prob) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int kWTap = BN * KC * 2 * 2;
+  const bool one = prob->passes == 1;   // single-pass product A_hi x W_hi: hi planes only
+  const int planes = one ? 1 : 2;
+  constexpr int kWPlane = BN * KC * 2;  // one weight plane of one tap
+  const int kWTap = kWPlane * planes;
   const int kTileH = prob->tile_h, kTileW = prob->tile_w;
   constexpr int kHaloBox = halo_box_bytes(KC), kHaloPlane = halo_plane_bytes(KC), kHaloStage = halo_stage_bytes(KC);
   const bool halo = prob->halo != 0;   // plan guarantees 16x8 tiles
   const int kAPlane = halo ? kHaloPlane : a_plane_bytes(KC, kTileH, kTileW);
-  const int kAStage = halo ? kHaloStage : a_stage_bytes(KC, kTileH, kTileW);
+  const int kAStage = planes * kAPlane;
+  (void)kHaloStage;
   const int kRowStep = kTileW * KC * 2;  // one tile row of pixels = tile_w/8 swizzle atoms
   constexpr bool kFused = BN <= 128;
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
@@ -135,11 +140,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       mbar_expect_tx(tail + 8u * (2 * kMaxRing), (uint32_t)nkb * kWTap);
       for (int kb = 0; kb < nkb; ++kb) {
         tma_load_2d(w_base + kb * kWTap, tm_w_hi, tail + 8u * (2 * kMaxRing), kb * KC, 0);
-        tma_load_2d(w_base + kb * kWTap + kWTap / 2, tm_w_lo, tail + 8u * (2 * kMaxRing), kb * KC, 0);
+        if (!one) tma_load_2d(w_base + kb * kWTap + kWPlane, tm_w_lo, tail + 8u * (2 * kMaxRing), kb * KC, 0);
       }
     }
     __syncwarp();
-    uint32_t ia = 0, iw = 0;
+    RingPos ra, rw;   // activation / weight ring positions
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int sp = tile / n_nt, n0 = (tile % n_nt) * BN;
       const int b = sp / tiles_per_img, rem = sp % tiles_per_img;
@@ -155,10 +160,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
               // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the (tile_w + 2)-px-wide halo
               const int cc = src_tab[2 * s + 1] + ch * KC;
               tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 - 1, ny0 - 1, nb);
-              tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 - 1, ny0 - 1, nb);
+              if (!one) tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 - 1, ny0 - 1, nb);
               if (!halo) {  // (the wide box already spans the halo)
                 tma_prefetch_4d(&prob->tm_a_hi[s], cc, nx0 + 1, ny0 - 1, nb);
-                tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 + 1, ny0 - 1, nb);
+                if (!one) tma_prefetch_4d(&prob->tm_a_lo[s], cc, nx0 + 1, ny0 - 1, nb);
               }
             }
         }
@@ -172,29 +177,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         for (int ch = 0; ch < nchunk; ++ch) {
           const int nst = halo ? 1 : 3;   // activation stages of this chunk: one wide halo box or three dx boxes
           for (int dx = 0; dx < nst; ++dx) {
-            const int st = ia % NA;
-            mbar_wait(tail + 8u * (kMaxRing + st), ((ia / NA) & 1u) ^ 1u);
+            const int st = ra.stage;
+            mbar_wait(tail + 8u * (kMaxRing + st), ra.phase ^ 1u);
             if (elect_one()) {
               const uint32_t sa = a_base + st * kAStage, bar = tail + 8u * st;
-              mbar_expect_tx(bar, halo ? 2u * kHaloBox : (uint32_t)kAStage);
+              mbar_expect_tx(bar, halo ? (uint32_t)(planes * kHaloBox) : (uint32_t)kAStage);
               tma_load_4d(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
-              tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              if (!one) tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
             }
             __syncwarp();
-            ++ia;
+            ra.advance(NA);
             if (!resident) {
               const int ntap = halo ? 9 : 3;   // weight taps consumed against this activation stage
               for (int t = 0; t < ntap; ++t, ++kb) {
-                const int ws = iw % NW;
-                mbar_wait(tail + 8u * (3 * kMaxRing + ws), ((iw / NW) & 1u) ^ 1u);
+                const int ws = rw.stage;
+                mbar_wait(tail + 8u * (3 * kMaxRing + ws), rw.phase ^ 1u);
                 if (elect_one()) {
                   const uint32_t sw = w_base + ws * kWTap, bar = tail + 8u * (2 * kMaxRing + ws);
                   mbar_expect_tx(bar, kWTap);
                   tma_load_2d(sw, tm_w_hi, bar, kb * KC, n0);
-                  tma_load_2d(sw + kWTap / 2, tm_w_lo, bar, kb * KC, n0);
+                  if (!one) tma_load_2d(sw + kWPlane, tm_w_lo, bar, kb * KC, n0);
                 }
                 __syncwarp();
-                ++iw;
+                rw.advance(NW);
               }
             }
           }
@@ -216,13 +221,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
     // Halo mode: one activation stage per chunk carries all nine taps; tap t = 3*dx + dy (the K order of the
     // packed weights) reads the box at byte offset (dy * 10 + dx) * 128, 8-row groups 1280 B apart.
-    auto run_items = [&](auto partial_tag, auto halo_tag) {
+    auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag) {
       constexpr bool kPartial = decltype(partial_tag)::value;
       constexpr bool kHalo = decltype(halo_tag)::value;
+      constexpr bool kOne = decltype(one_tag)::value;   // single-pass product
       constexpr int kStageTaps = kHalo ? 9 : 3;   // taps served by one activation stage
       constexpr int kSrcStages = kHalo ? 1 : 3;   // activation stages per chunk
       const int nab = nkb / kStageTaps;           // activation stages per tile
-      uint32_t ia = 0, iw = 0, it = 0;
+      RingPos ra, rw;   // activation / weight ring positions
+      uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         mbar_wait(tail + 8u * (4 * kMaxRing + 2 + acc), ((it >> 1) & 1u) ^ 1u);
@@ -240,8 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             --src_left;
             ksteps = src_tab[2 * kMaxSrc + src_i];
           }
-          const int st = ia % NA;
-          mbar_wait(tail + 8u * st, (ia / NA) & 1u);
+          const int st = ra.stage;
+          mbar_wait(tail + 8u * st, ra.phase);
           tc_fence_after();
           const uint32_t sa = a_base + st * kAStage;
           for (int t = 0; t < kStageTaps; ++t, ++kb) {
@@ -250,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             if (resident) {
               sw = w_base + kb * kWTap;
             } else {
-              ws = iw % NW;
-              mbar_wait(tail + 8u * (2 * kMaxRing + ws), (iw / NW) & 1u);
+              ws = rw.stage;
+              mbar_wait(tail + 8u * (2 * kMaxRing + ws), rw.phase);
               tc_fence_after();
               sw = w_base + ws * kWTap;
             }
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
                 a_hi = make_desc_kc<KC>(sa + t * kRowStep);
                 a_lo = make_desc_kc<KC>(sa + kAPlane + t * kRowStep);
               }
-              const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWTap / 2);
+              const uint64_t w_hi = make_desc_kc<KC>(sw), w_lo = make_desc_kc<KC>(sw + kWPlane);
               const uint32_t first = (kb == 0) ? 0u : 1u;
   #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
@@ -274,7 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
                   if (k >= ksteps) break;
                 }
                 const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                if constexpr (kFused) {
+                if constexpr (kOne) {
+                  umma(d_tmem, a_hi + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
+                } else if constexpr (kFused) {
                   umma(d_tmem, a_hi + adv, w_hi + adv, idesc2, k == 0 ? first : 1u);  // N = 2*BN: [W_hi ; W_lo]
                   umma(d_tmem, a_lo + adv, w_hi + adv, idesc, 1u);
                 } else {
@@ -288,19 +297,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
               if (t == kStageTaps - 1 && ab == nab - 1) umma_commit(tail + 8u * (4 * kMaxRing + acc));
             }
             __syncwarp();
-            if (!resident) ++iw;
+            if (!resident) rw.advance(NW);
           }
-          ++ia;
+          ra.advance(NA);
         }
       }
     };
-    if (halo) {
-      if (any_partial) run_items(std::true_type{}, std::true_type{});
-      else run_items(std::false_type{}, std::true_type{});
-    } else {
-      if (any_partial) run_items(std::true_type{}, std::false_type{});
-      else run_items(std::false_type{}, std::false_type{});
-    }
+    auto run_pass = [&](auto one_tag) {
+      if (halo) {
+        if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag);
+        else run_items(std::false_type{}, std::true_type{}, one_tag);
+      } else {
+        if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag);
+        else run_items(std::false_type{}, std::false_type{}, one_tag);
+      }
+    };
+    if (one) run_pass(std::true_type{});
+    else run_pass(std::false_type{});
   } else {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -316,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     sp_t* const pool_lo = prob->pool_lo;
     const int pool_C = prob->pool_C;
     const bool do_pool = pool_hi != nullptr;
+    const bool lo_skip = prob->out_lo_skip != 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         if (n0 + cc * 16 >= cout) break;
         uint32_t v[16];
         tmem_ld16(t_addr + (uint32_t)(cc * 16), v);
-        if constexpr (kFused) {
+        if (kFused && !one) {
           uint32_t u[16];
           tmem_ld16(t_addr + (uint32_t)(BN + cc * 16), u);
           tmem_ld_wait();
@@ -350,7 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             float x = __uint_as_float(v[j]) + bias_smem[n0 + cc * 16 + j];
             f[j] = act ? leaky(x) : x;
           }
-          if (valid) pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
+          if (valid) {
+            if (lo_skip) pack_store16_hi(f, oh + cc * 16);
+            else pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
+          }
           if (do_pool) {
             float pf[16];
 #pragma unroll
@@ -382,8 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
 
 int smem_bytes_for(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
-  const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk) : h.v2_nw * w_tap_bytes(bn, h.kchunk);
-  return h.v2_na * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo) + w + kFixedBytes;
+  const int planes = h.passes == 1 ? 1 : 2;
+  const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk, planes) : h.v2_nw * w_tap_bytes(bn, h.kchunk, planes);
+  return h.v2_na * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo, planes) + w + kFixedBytes;
 }
 
 }  // namespace
@@ -413,15 +431,16 @@ void conv3x3_tc_pick_tile(int H, int W, int B, int cout, int num_sms, int& tile_
 void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int bn = h.bn;
   const int nkb = h.ktot / h.kchunk;
-  const int wtap = w_tap_bytes(bn, h.kchunk);
+  const int planes = h.passes == 1 ? 1 : 2;
+  const int wtap = w_tap_bytes(bn, h.kchunk, planes);
   const int w_all = nkb * wtap;
   const bool can_resident = h.cout <= bn;
   // wide halo (the engine allows it per chunk size): 16x8 tiles only; resident weights win when both do not fit
   if (h.halo && (h.tile_h != 16 || h.tile_w != 8 ||
-                 (can_resident && w_all + 2 * a_stage_bytes(h.kchunk, h.tile_h, h.tile_w) + kFixedBytes <= kSmemLimit &&
-                  w_all + 2 * halo_stage_bytes(h.kchunk) + kFixedBytes > kSmemLimit)))
+                 (can_resident && w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 0, planes) + kFixedBytes <= kSmemLimit &&
+                  w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 1, planes) + kFixedBytes > kSmemLimit)))
     h.halo = 0;
-  const int kAStage = a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo);
+  const int kAStage = a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo, planes);
   h.v2_resident = 0;
   if (can_resident && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;

@@ -48,12 +48,16 @@ constexpr int kHaloW = kTileW + 2;
 __host__ __device__ constexpr int halo_box_bytes(int kc) { return (kTileH + 2) * kHaloW * kc * 2; }  // 23,040 (KC 64)
 __host__ __device__ constexpr int halo_plane_bytes(int kc) { return (halo_box_bytes(kc) + 1023) & ~1023; }  // 1 KiB-aligned planes
 __host__ __device__ constexpr int halo_stage_bytes(int kc) { return 2 * halo_plane_bytes(kc); }  // 46 KiB vs 3 x 36 KiB
-__host__ __device__ constexpr int a_stage_bytes2h(int kc, int halo) { return halo ? halo_stage_bytes(kc) : a_stage_bytes2(kc); }
+// `planes` = 2 (hi + lo) or 1 (single-pass layers load the hi planes only)
+__host__ __device__ constexpr int a_stage_bytes2h(int kc, int halo, int planes = 2) {
+  return (halo ? halo_stage_bytes(kc) : a_stage_bytes2(kc)) / 2 * planes;
+}
 // bytes of one weight tap per CTA: unfused = half of W_hi + half of W_lo; fused (BN <= 64) = one full
 // plane (W_hi in the leader, W_lo in the peer) + this CTA's half of W_hi
 __host__ __device__ constexpr bool pair_fused(int bn) { return bn <= 64; }
-__host__ __device__ constexpr int w_half_tap_bytes(int bn, int kc) {
-  return pair_fused(bn) ? (bn + bn / 2) * kc * 2 : (bn / 2) * kc * 2 * 2;
+// single-pass: this CTA's half of the W_hi rows only
+__host__ __device__ constexpr int w_half_tap_bytes(int bn, int kc, int planes = 2) {
+  return planes == 1 ? (bn / 2) * kc * 2 : pair_fused(bn) ? (bn + bn / 2) * kc * 2 : (bn / 2) * kc * 2 * 2;
 }
 
 template <int BN, int KC>
@@ -65,7 +69,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   constexpr bool kFused = pair_fused(BN);
   constexpr int kWHalf = (BN / 2) * KC * 2;   // one plane, half of the rows
   constexpr int kWFull = BN * KC * 2;         // one plane, all rows of the N tile
-  constexpr int kWTap = w_half_tap_bytes(BN, KC);
   constexpr int kRowStep = kTileW * KC * 2;
   constexpr int kHaloBox = halo_box_bytes(KC), kHaloPlane = halo_plane_bytes(KC), kHaloStage = halo_stage_bytes(KC);
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
@@ -77,7 +80,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int NA = prob->v2_na, NW = prob->v2_nw;
   const bool resident = prob->v2_resident != 0;
   const bool halo = prob->halo != 0;
-  const int a_stage = halo ? kHaloStage : kAStage;
+  const bool one = prob->passes == 1;   // single-pass product A_hi x W_hi: hi planes only
+  const int planes = one ? 1 : 2;
+  const int kWTap = w_half_tap_bytes(BN, KC, planes);
+  const int lo_plane = halo ? kHaloPlane : kAPlane;
+  const int a_stage = planes * lo_plane;
+  (void)kAStage; (void)kHaloStage;
   const int nsrc = prob->nsrc;
   const int tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
   const int pairs_y = (tiles_y + 1) / 2;
@@ -149,7 +157,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t bar = map_to_cta(w_full(0), 0);
         if (leader) mbar_expect_tx(w_full(0), 2u * (uint32_t)nkb * kWTap);   // both CTAs' halves
         for (int kb = 0; kb < nkb; ++kb) {
-          if constexpr (kFused) {
+          if (one) {
+            tma_load_2d_2sm(w_base + kb * kWTap, tm_w_hi, bar, kb * KC, n_half);
+          } else if constexpr (kFused) {
             tma_load_2d_2sm(w_base + kb * kWTap, leader ? tm_w_full_hi : tm_w_full_lo, bar, kb * KC, 0);
             tma_load_2d_2sm(w_base + kb * kWTap + kWFull, tm_w_hi, bar, kb * KC, n_half);
           } else {
@@ -160,7 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
       __syncwarp();
     }
-    uint32_t ia = 0, iw = 0;
+    RingPos ra, rw;   // activation / weight ring positions
     for (int item = item0; item < nitems; item += item_step) {
       const int sp = item / n_nt, n0 = (item % n_nt) * BN;
       const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
@@ -174,33 +184,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           // activation stages of this chunk: one wide halo box, or three dx-shifted boxes
           const int nst = halo ? 1 : 3;
           for (int dx = 0; dx < nst; ++dx) {
-            const int st = ia % NA;
-            mbar_wait(a_empty(st), ((ia / NA) & 1u) ^ 1u);
+            const int st = ra.stage;
+            mbar_wait(a_empty(st), ra.phase ^ 1u);
             if (elect_one()) {
               const uint32_t sa = a_base + st * a_stage;
               const uint32_t bar = map_to_cta(a_full(st), 0);
               if (halo) {
-                if (leader) mbar_expect_tx(a_full(st), 4u * kHaloBox);   // two planes x two CTAs
+                if (leader) mbar_expect_tx(a_full(st), 2u * planes * kHaloBox);   // planes x two CTAs
                 tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
-                tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
+                if (!one) tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
               } else {
-                if (leader) mbar_expect_tx(a_full(st), 2u * kAStage);
+                if (leader) mbar_expect_tx(a_full(st), 2u * planes * kAPlane);
                 tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
-                tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+                if (!one) tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
               }
             }
             __syncwarp();
-            ++ia;
+            ra.advance(NA);
             if (!resident) {
               const int ntap = halo ? 9 : 3;   // weight taps consumed against this activation stage
               for (int t = 0; t < ntap; ++t, ++kb) {
-                const int ws = iw % NW;
-                mbar_wait(w_empty(ws), ((iw / NW) & 1u) ^ 1u);
+                const int ws = rw.stage;
+                mbar_wait(w_empty(ws), rw.phase ^ 1u);
                 if (elect_one()) {
                   const uint32_t sw = w_base + ws * kWTap;
                   const uint32_t bar = map_to_cta(w_full(ws), 0);
                   if (leader) mbar_expect_tx(w_full(ws), 2u * kWTap);
-                  if constexpr (kFused) {
+                  if (one) {
+                    tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n0 + n_half);
+                  } else if constexpr (kFused) {
                     tma_load_2d_2sm(sw, leader ? tm_w_full_hi : tm_w_full_lo, bar, kb * KC, n0);
                     tma_load_2d_2sm(sw + kWFull, tm_w_hi, bar, kb * KC, n0 + n_half);
                   } else {
@@ -209,7 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   }
                 }
                 __syncwarp();
-                ++iw;
+                rw.advance(NW);
               }
             }
           }
@@ -231,15 +243,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // groups (one tile row each) 1280 B apart.
       bool any_partial = false;
       for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
-      auto run_items = [&](auto partial_tag, auto halo_tag) {
+      auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag) {
         constexpr bool kPartial = decltype(partial_tag)::value;
         constexpr bool kHalo = decltype(halo_tag)::value;
+        constexpr bool kOne = decltype(one_tag)::value;   // single-pass product
         constexpr int kStageTaps = kHalo ? 9 : 3;       // taps served by one activation stage
         constexpr int kSrcStages = kHalo ? 1 : 3;       // activation stages per chunk
-        constexpr int kStageBytes = kHalo ? kHaloStage : kAStage;
         constexpr int kLoPlane = kHalo ? kHaloPlane : kAPlane;
+        constexpr int kStageBytes = (kOne ? 1 : 2) * kLoPlane;
         const int nab = nkb / kStageTaps;
-        uint32_t ia = 0, iw = 0, it = 0;
+        RingPos ra, rw;   // activation / weight ring positions
+        uint32_t it = 0;
         for (int item = item0; item < nitems; item += item_step, ++it) {
           const uint32_t acc = it & 1u;
           mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
@@ -257,8 +271,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               --src_left;
               ksteps = src_tab[2 * kMaxSrc + src_i];
             }
-            const int st = ia % NA;
-            mbar_wait(a_full(st), (ia / NA) & 1u);
+            const int st = ra.stage;
+            mbar_wait(a_full(st), ra.phase);
             tc_fence_after();
             const uint32_t sa = a_base + st * kStageBytes;
             for (int t = 0; t < kStageTaps; ++t, ++kb) {
@@ -267,8 +281,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               if (resident) {
                 sw = w_base + kb * kWTap;
               } else {
-                ws = iw % NW;
-                mbar_wait(w_full(ws), (iw / NW) & 1u);
+                ws = rw.stage;
+                mbar_wait(w_full(ws), rw.phase);
                 tc_fence_after();
                 sw = w_base + ws * kWTap;
               }
@@ -284,7 +298,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   a_lo = make_desc_kc<KC>(sa + kLoPlane + t * kRowStep);
                 }
                 const uint32_t first = (kb == 0) ? 0u : 1u;
-                if constexpr (kFused) {
+                if constexpr (kOne) {
+                  // each CTA holds its half of the W_hi rows at `sw`
+                  const uint64_t w_h = make_desc_kc<KC>(sw);
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    if constexpr (kPartial) {
+                      if (k >= ksteps) break;
+                    }
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    umma_2sm(d_tmem, a_hi + adv, w_h + adv, idesc, k == 0 ? first : 1u);
+                  }
+                } else if constexpr (kFused) {
                   // region X (leader: W_hi, peer: W_lo) is the 2*BN-row operand; region Y = halves of W_hi
                   const uint64_t w_x = make_desc_kc<KC>(sw), w_y = make_desc_kc<KC>(sw + kWFull);
 #pragma unroll
@@ -314,19 +339,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 if (t == kStageTaps - 1 && ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
               }
               __syncwarp();
-              if (!resident) ++iw;
+              if (!resident) rw.advance(NW);
             }
-            ++ia;
+            ra.advance(NA);
           }
         }
       };
-      if (halo) {
-        if (any_partial) run_items(std::true_type{}, std::true_type{});
-        else run_items(std::false_type{}, std::true_type{});
-      } else {
-        if (any_partial) run_items(std::true_type{}, std::false_type{});
-        else run_items(std::false_type{}, std::false_type{});
-      }
+      auto run_pass = [&](auto one_tag) {
+        if (halo) {
+          if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag);
+          else run_items(std::false_type{}, std::true_type{}, one_tag);
+        } else {
+          if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag);
+          else run_items(std::false_type{}, std::false_type{}, one_tag);
+        }
+      };
+      if (one) run_pass(std::true_type{});
+      else run_pass(std::false_type{});
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================
@@ -341,6 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     sp_t* const pool_lo = prob->pool_lo;
     const int pool_C = prob->pool_C;
     const bool do_pool = pool_hi != nullptr;
+    const bool lo_skip = prob->out_lo_skip != 0;
     const uint32_t t_empty_leader0 = map_to_cta(t_empty(0), 0), t_empty_leader1 = map_to_cta(t_empty(1), 0);
     uint32_t it = 0;
     for (int item = item0; item < nitems; item += item_step, ++it) {
@@ -360,7 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (n0 + cc * 16 >= cout) break;
         uint32_t v[16];
         tmem_ld16(t_addr + (uint32_t)(cc * 16), v);
-        if constexpr (kFused) {
+        if (kFused && !one) {
           uint32_t u[16];
           tmem_ld16(t_addr + (uint32_t)(BN + cc * 16), u);
           tmem_ld_wait();
@@ -376,7 +406,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             float x = __uint_as_float(v[j]) + bias_smem[n0 + cc * 16 + j];
             f[j] = act ? leaky(x) : x;
           }
-          if (valid) pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
+          if (valid) {
+            if (lo_skip) pack_store16_hi(f, oh + cc * 16);
+            else pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
+          }
           if (do_pool) {
             float pf[16];
 #pragma unroll
@@ -408,8 +441,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
 int smem_bytes_for2(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
-  const int w = h.v2_resident ? nkb * w_half_tap_bytes(bn, h.kchunk) : h.v2_nw * w_half_tap_bytes(bn, h.kchunk);
-  return h.v2_na * a_stage_bytes2h(h.kchunk, h.halo) + w + kFixedBytes;
+  const int planes = h.passes == 1 ? 1 : 2;
+  const int wt = w_half_tap_bytes(bn, h.kchunk, planes);
+  const int w = h.v2_resident ? nkb * wt : h.v2_nw * wt;
+  return h.v2_na * a_stage_bytes2h(h.kchunk, h.halo, planes) + w + kFixedBytes;
 }
 
 }  // namespace
@@ -422,14 +457,15 @@ bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
   if (h.kchunk == 32 && bn != 32) return false;
   if (h.cout % bn) return false;            // whole N tiles only (the half-row boxes must not straddle Cout)
   const int nkb = h.ktot / h.kchunk;
-  const int wtap = w_half_tap_bytes(bn, h.kchunk);
+  const int planes = h.passes == 1 ? 1 : 2;
+  const int wtap = w_half_tap_bytes(bn, h.kchunk, planes);
   const int w_all = nkb * wtap;
   const bool can_resident = h.cout <= bn && 2 * (long)nkb * wtap < (1 << 20);
   // wide halo (the engine allows it per chunk size): resident weights win when both do not fit
-  if (h.halo && can_resident && w_all + 2 * a_stage_bytes2(h.kchunk) + kFixedBytes <= kSmemLimit &&
-      w_all + 2 * halo_stage_bytes(h.kchunk) + kFixedBytes > kSmemLimit)
+  if (h.halo && can_resident && w_all + 2 * a_stage_bytes2h(h.kchunk, 0, planes) + kFixedBytes <= kSmemLimit &&
+      w_all + 2 * a_stage_bytes2h(h.kchunk, 1, planes) + kFixedBytes > kSmemLimit)
     h.halo = 0;
-  const int a_stage = a_stage_bytes2h(h.kchunk, h.halo);
+  const int a_stage = a_stage_bytes2h(h.kchunk, h.halo, planes);
   h.v2_resident = 0;
   if (can_resident && w_all + 2 * a_stage + kFixedBytes <= kSmemLimit) {
     h.v2_resident = 1;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
 
   // problem fields -> registers once (asm "memory" clobbers would otherwise reload them from global)
   const int nsrc = prob->nsrc, ntaps = prob->ntaps, cout = prob->cout, epi_mode = prob->epi_mode;
+  const bool one = prob->passes == 1;   // single-pass product: hi planes only
   const int tile_h = prob->tile_h, tile_w = prob->tile_w, tiles_x = prob->tiles_x, tiles_y = prob->tiles_y;
 
   // tile coordinates
@@ -131,12 +132,14 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (elect_one()) {
             const uint32_t sa = base + stage * Cfg::kStageBytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            mbar_expect_tx(full_bar(stage), one ? (uint32_t)(kABytes + Cfg::kWBytes) : (uint32_t)Cfg::kStageBytes);
             const int cc = c_off + ch * KC;
             tma_load_4d(sa, tm_hi, full_bar(stage), cc, xx, yy, b);
-            tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, b);
             tma_load_2d(sa + 2 * kABytes, tm_w_hi, full_bar(stage), kb * KC, n0);
-            tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * KC, n0);
+            if (!one) {
+              tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, b);
+              tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * KC, n0);
+            }
           }
           __syncwarp();
         }
@@ -159,7 +162,9 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 elements x 2 B = 32 B along K
-          if constexpr (Cfg::kFused) {
+          if (one) {
+            umma(tmem_base, a_hi + adv, w_hi + adv, idesc, k == 0 ? first : 1u);
+          } else if constexpr (Cfg::kFused) {
             umma(tmem_base, a_hi + adv, w_hi + adv, idesc2, k == 0 ? first : 1u);  // [W_hi ; W_lo]
             umma(tmem_base, a_lo + adv, w_hi + adv, idesc, 1u);
           } else {
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
     const int act = prob->act;
     sp_t* oh = prob->out_hi + opix * prob->out_C + prob->out_c_off + n0;
     sp_t* ol = prob->out_lo + opix * prob->out_C + prob->out_c_off + n0;
+    const bool lo_skip = prob->out_lo_skip != 0;
     const float* head_vup = prob->head_vup;
     float* head_res = prob->head_res;
     float* head_v = prob->head_v;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
-        if constexpr (Cfg::kFused) {
+        if (Cfg::kFused && !one) {
           uint32_t u[32];
           tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
           tmem_ld_wait();
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
         if (n0 + cc * 32 >= cout) break;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(cc * 32), v);
-        if constexpr (Cfg::kFused) {
+        if (Cfg::kFused && !one) {
           uint32_t u[32];
           tmem_ld32(t_addr + (uint32_t)(BN + cc * 32), u);
           tmem_ld_wait();
@@ -248,7 +254,8 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
               float x = __uint_as_float(v[g * 16 + j]) + bias_smem[cc * 32 + g * 16 + j];
               f[j] = act ? leaky(x) : x;
             }
-            pack_store16(f, oh + cc * 32 + g * 16, ol + cc * 32 + g * 16);
+            if (lo_skip) pack_store16_hi(f, oh + cc * 32 + g * 16);
+            else pack_store16(f, oh + cc * 32 + g * 16, ol + cc * 32 + g * 16);
           }
         }
       }

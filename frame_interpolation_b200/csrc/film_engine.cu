@@ -42,6 +42,37 @@ struct Error {
   int code;
   std::string msg;
 };
+
+// ----------------------------------------------------------------------------------------
+// Precision plan.  Every tensor-core conv call site belongs to a STAGE; bit s of the plan's one-pass mask
+// selects the single-pass product (A_hi x W_hi: fp16 operands, fp32 accumulate) for stage s, otherwise the
+// three-pass split product (fp32-grade).  The flow heads and the RGB head are always three-pass / fp32.
+// The default mask is the outcome of the measured per-stage error study (tools/precision_study.py,
+// profiles/r2_precision_study_1080p.md).
+// ----------------------------------------------------------------------------------------
+enum Stage {
+  ST_FE_I0_K01 = 0, ST_FE_I0_K23, ST_FE_I0_K45, ST_FE_I0_K67,  // sub-tree of image level 0: conv pairs
+  ST_FE_I1, ST_FE_I2, ST_FE_I3P,                                // sub-trees of image levels 1, 2, 3..6
+  ST_FLOW_L0,                                                    // + pyramid level (7 levels): conv_0..2
+  ST_FUS = ST_FLOW_L0 + kLevels,                                 // + 3 * fusion level + conv index
+  ST_COUNT = ST_FUS + 3 * (kFusionLevels - 1),
+  ST_NONE = -1
+};
+static std::string stage_name(int s) {
+  static const char* fe[] = {"fe_i0_k01", "fe_i0_k23", "fe_i0_k45", "fe_i0_k67", "fe_i1", "fe_i2", "fe_i3p"};
+  if (s < 0 || s >= ST_COUNT) return "";
+  if (s < ST_FLOW_L0) return fe[s];
+  if (s < ST_FUS) return "flow_L" + std::to_string(s - ST_FLOW_L0);
+  return "fus" + std::to_string((s - ST_FUS) / 3) + "_c" + std::to_string((s - ST_FUS) % 3);
+}
+static int fe_stage(int image_level, int conv_k) {
+  if (image_level == 0) return ST_FE_I0_K01 + conv_k / 2;
+  return image_level == 1 ? ST_FE_I1 : image_level == 2 ? ST_FE_I2 : ST_FE_I3P;
+}
+// default: flow levels 0-4, the three deeper conv pairs of the level-0 sub-tree, fusion levels 2 and 3
+constexpr uint32_t kDefaultOnepassMask =
+    (1u << ST_FE_I0_K23) | (1u << ST_FE_I0_K45) | (1u << ST_FE_I0_K67) |
+    (0x1Fu << ST_FLOW_L0) | (0x3Fu << (ST_FUS + 6));
 #define FILM_CUDA(expr)                                                                       \
   do {                                                                                        \
     cudaError_t e__ = (expr);                                                                 \
@@ -431,6 +462,7 @@ struct Plan {
   int conv_impl;
   int conv3x3_v2 = 1, num_sms = 148, conv3x3_2cta = 0;
   int conv3x3_halo = 0;  // 1: pair kernel, 2: + single-CTA persistent kernel, 3: + 32-channel-chunk layers
+  uint32_t onepass_mask = 0;  // precision plan: stages on the single-pass product
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -511,10 +543,11 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 // Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
 static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
                        const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
-                       int sy = 1, int sx = 1, int oy = 0, int ox = 0, const SplitBuf* pool_out = nullptr,
+                       int stage, int sy = 1, int sx = 1, int oy = 0, int ox = 0, const SplitBuf* pool_out = nullptr,
                        bool no_op = false) {
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
+  cp.passes = (stage >= 0 && P.conv_impl == 0 && ((P.onepass_mask >> stage) & 1u)) ? 1 : 3;
   const SplitBuf* s0 = sources[0].buf;
   cp.nsrc = (int)sources.size();
   if (cp.nsrc != (int)pc.src_chunks.size()) throw Error{FILM_ERR_WEIGHTS, "source count mismatch"};
@@ -640,7 +673,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   double k_issued = 0;  // skipped all-zero k-steps are not issued work
   for (size_t si = 0; si < pc.src_chunks.size(); ++si)
     k_issued += (double)pc.src_chunks[si] * pc.ntaps * ((v2 || pair) ? pc.src_ksteps[si] * 16 : pc.kchunk);
-  P.mma_flops += 3.0 * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * k_issued *
+  P.mma_flops += (double)cp.passes * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * k_issued *
                  (double)(((pc.cout + bn - 1) / bn) * bn);
   if (no_op) return idx;  // the caller launches this problem as part of a group
   Plan* pp = &P;
@@ -655,9 +688,11 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
 }
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
-                                        int conv3x3_v2, int num_sms, int conv3x3_2cta, int conv3x3_halo) {
+                                        int conv3x3_v2, int num_sms, int conv3x3_2cta, int conv3x3_halo,
+                                        uint32_t onepass_mask) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
+  P.onepass_mask = onepass_mask;
   P.h = h;
   P.w = w;
   P.conv_impl = conv_impl;
@@ -675,8 +710,11 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.W = w + pw;
   P.off_y = ph / 2;
   P.off_x = pw / 2;
+  // The reference graph accepts any size (VALID pooling floors, flows and fusion resize to the level size);
+  // this engine implements the 64-aligned case only -- the CLI default (--align 64, eval/interpolator_cli.py:103).
   if (P.H % 64 || P.W % 64)
-    throw Error{FILM_ERR_ARG, "padded frame size must be a multiple of 64 (2^(pyramid_levels-1)); use align=64"};
+    throw Error{FILM_ERR_UNSUPPORTED,
+                "padded frame size must be a multiple of 64 (2^(pyramid_levels-1)) in this engine; use align=64"};
   int Hs[kLevels], Ws[kLevels];
   for (int l = 0; l < kLevels; ++l) {
     Hs[l] = P.H >> l;
@@ -730,7 +768,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         P.add_op(2, "fe_split32@L" + std::to_string(r),
                  [=](cudaStream_t st) { return launch_image_to_split32(im, 2, hh, ww, im32->hi, im32->lo, st); }, 0,
                  2.0 * hh * ww * (12 + 32.0));
-        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe0_3x3, {{im32, 0}}, 1, t1, 0);
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe0_3x3, {{im32, 0}}, 1, t1, 0, fe_stage(i, 0));
       } else if (j == 0 && P.conv_impl == 0) {
         // generic-kernel variant: im2col-lite (27 -> 32 channels) + a 1x1 conv, K = 32
         const float* im = img[i];
@@ -739,7 +777,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         P.add_op(2, "fe_im2col@L" + std::to_string(r),
                  [=](cudaStream_t st) { return launch_im2col3x3(im, 2, hh, ww, col->hi, col->lo, st); }, 0,
                  2.0 * hh * ww * (12 + 128.0));
-        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe[0], {{col, 0}}, 1, t1, 0);
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe[0], {{col, 0}}, 1, t1, 0, fe_stage(i, 0));
       } else if (j == 0) {
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
@@ -750,7 +788,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
                  2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 + 64) * 4.0);
       } else {
         add_conv(P, "fe_conv" + std::to_string(2 * j) + "@L" + std::to_string(r), 9.0 * (c / 2) * c, M.fe[2 * j],
-                 {{pooled, 0}}, 1, t1, 0);
+                 {{pooled, 0}}, 1, t1, 0, fe_stage(i, 2 * j));
       }
       // second conv of the pair writes straight into the cascaded feature tensor slice
       // (replaces the tf.concat at feature_extractor.py:191)
@@ -758,7 +796,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       const bool fuse_pool = (j < depth - 1) && P.conv_impl == 0 && P.conv3x3_v2;
       if (j < depth - 1) pool_target = P.split(2, Hs[r + 1], Ws[r + 1], c);
       add_conv(P, "fe_conv" + std::to_string(2 * j + 1) + "@L" + std::to_string(r), 9.0 * c * c, M.fe[2 * j + 1],
-               {{t1, 0}}, 1, feat[r], slice_off[j], 1, 1, 0, 0, fuse_pool ? pool_target : nullptr);
+               {{t1, 0}}, 1, feat[r], slice_off[j], fe_stage(i, 2 * j + 1), 1, 1, 0, 0, fuse_pool ? pool_target : nullptr);
       tok_feat[i][j] = P.new_token();
       P.signal_last(tok_feat[i][j]);
       if (fuse_pool) {
@@ -828,9 +866,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);
     const std::string lt = "@L" + std::to_string(l);
-    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0);
-    add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0);
-    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0);
+    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0, ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l);
     if (P.conv_impl == 1) {
       // CUDA-core validation path keeps the standalone fp32 head kernel
       const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
@@ -843,7 +881,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     } else {
       // conv_3 (1x1, nf -> nf/2) on the tensor cores; conv_4 + residual add in its epilogue
       const size_t ci = add_conv(P, "flow_head" + lt, 1.0 * nf * (nf / 2) + (nf / 2) * 2.0, M.flow_c3[p], {{c2, 0}}, 1,
-                                 nullptr, 0);
+                                 nullptr, 0, ST_NONE);
       ConvProblem& hp = P.h_probs[ci];
       hp.epi_mode = 1;
       hp.head_w4 = M.flow_w4[p];
@@ -909,7 +947,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       size_t first = 0;
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
-          const size_t ci = add_conv(P, "", 0, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px, nullptr, true);
+          const size_t ci = add_conv(P, "", 0, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i, 2, 2, py, px, nullptr, true);
           if (py == 0 && px == 0) first = ci;
         }
       P.h_probs[first].group = 4;
@@ -922,13 +960,13 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px)
           add_conv(P, "fusion_up" + std::to_string(py * 2 + px) + "@L" + std::to_string(i),
-                   4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, 2, 2, py, px);
+                   4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i, 2, 2, py, px);
     }
     SplitBuf* f1 = P.split(1, hh, ww, cpad);
     SplitBuf* f2 = P.split(1, hh, ww, cpad);
     add_conv(P, "fusion_conv1@L" + std::to_string(i), 9.0 * M.fus_c1[i].cin_ref * nf, M.fus_c1[i],
-             {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0);
-    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0);
+             {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0, ST_FUS + 3 * i + 1);
+    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0, ST_FUS + 3 * i + 2);
     net = f2;
     P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
     P.debug["fusion_up/" + std::to_string(i)] = DebugTensor{true, up->hi, up->lo, (int64_t)hh * ww, up->C, 0, nf};
@@ -1009,6 +1047,7 @@ struct film_handle {
   int conv3x3_2cta = 1;  // CTA-pair (cta_group::2) kernel for streamed-weight 3x3 convs on the large levels
   int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
                          // persistent kernels (default), 3 also the 32-channel-chunk layers (experimental)
+  uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
@@ -1016,10 +1055,20 @@ struct film_handle {
 
 static std::string g_create_error;
 
-static int fail(film_handle* h, const Error& e) {
-  if (h) h->err = e.msg; else g_create_error = e.msg;
+static int fail(film_handle* h, const Error& e) noexcept {
+  try {
+    if (h) h->err = e.msg; else g_create_error = e.msg;
+  } catch (...) {
+  }
   return e.code;
 }
+// No C++ exception may unwind through an extern "C" entry point into the caller (ctypes / cgo / JNI):
+// everything is turned into a status code; film_last_error() carries the text.
+#define FILM_CATCH_ALL(h)                                                                                     \
+  catch (const Error& e) { return fail(h, e); }                                                               \
+  catch (const std::bad_alloc&) { return fail(h, Error{FILM_ERR_CUDA, "out of host memory"}); }               \
+  catch (const std::exception& e) { return fail(h, Error{FILM_ERR_CUDA, std::string("internal error: ") + e.what()}); } \
+  catch (...) { return fail(h, Error{FILM_ERR_CUDA, "unknown internal error"}); }
 
 // Enqueues the whole schedule with `origin` as lane 0: fork the other lanes from it, express
 // cross-lane dependencies with events, join everything back into `origin`.  Works both eagerly and
@@ -1065,21 +1114,22 @@ static void drop_plans(film_handle* h) {
 
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
-  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo);
+  snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p;
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo);
-  } catch (const Error&) {
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask);
+  } catch (const Error& e0) {
+    if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
     // them, drop the cache and retry once before giving up.
     if (h->plans.empty()) throw;
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo);
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask);
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1132,7 +1182,8 @@ static void run_plan(film_handle* h, Plan* P, cudaStream_t st) {
 extern "C" {
 
 const char* film_version(void) {
-  return "film_b200 0.1 sm_100a split=" FILM_SPLIT_NAME " mma=tcgen05.kind::f16 3-pass (hi*hi+hi*lo+lo*hi)";
+  return "film_b200 0.2 sm_100a split=" FILM_SPLIT_NAME
+         " mma=tcgen05.kind::f16, per-stage precision plan: 3-pass (hi*hi+hi*lo+lo*hi) or 1-pass (hi*hi)";
 }
 
 int film_create(film_handle** out, const char* weights_path, int device_ordinal) {
@@ -1163,6 +1214,7 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     FILM_CUDA(conv3x3_tc2_configure());
     if (const char* e2 = getenv("FILM_2CTA")) h->conv3x3_2cta = atoi(e2);
     if (const char* e3 = getenv("FILM_HALO")) h->conv3x3_halo = atoi(e3);
+    if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
     h->model.reset(new Model);
@@ -1170,9 +1222,17 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     *out = h;
     return FILM_OK;
   } catch (const Error& e) {
-    g_create_error = e.msg;
+    fail(nullptr, e);
     if (h) film_destroy(h);
     return e.code;
+  } catch (const std::exception& e) {
+    fail(nullptr, Error{FILM_ERR_CUDA, std::string("internal error: ") + e.what()});
+    if (h) film_destroy(h);
+    return FILM_ERR_CUDA;
+  } catch (...) {
+    fail(nullptr, Error{FILM_ERR_CUDA, "unknown internal error"});
+    if (h) film_destroy(h);
+    return FILM_ERR_CUDA;
   }
 }
 
@@ -1204,6 +1264,7 @@ const char* film_last_error(film_handle* h) { return h ? h->err.c_str() : g_crea
 
 int film_set_option(film_handle* h, const char* name, int value) {
   if (!h || !name) return FILM_ERR_ARG;
+  try {
   std::string n(name);
   if (n == "conv_impl") h->conv_impl = value;
   else if (n == "use_graph") h->use_graph = value;
@@ -1213,11 +1274,39 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "conv3x3_v2") h->conv3x3_v2 = value;
   else if (n == "conv3x3_2cta") h->conv3x3_2cta = value;
   else if (n == "conv3x3_halo") h->conv3x3_halo = value;
+  else if (n == "onepass_mask") h->onepass_mask = (uint32_t)value & ((1u << ST_COUNT) - 1u);
+  else if (n == "onepass_default") h->onepass_mask = kDefaultOnepassMask;
   else if (n == "clear_plans") drop_plans(h);
   else {
     h->err = "unknown option " + n;
     return FILM_ERR_ARG;
   }
+  return FILM_OK;
+  }
+  FILM_CATCH_ALL(h)
+}
+
+int film_stage_count(void) { return ST_COUNT; }
+
+int film_stage_name(int stage, char* buf, int buf_size) {
+  if (!buf || buf_size < 1 || stage < 0 || stage >= ST_COUNT) return FILM_ERR_ARG;
+  try {
+    const std::string n = stage_name(stage);
+    snprintf(buf, (size_t)buf_size, "%s", n.c_str());
+    return FILM_OK;
+  } catch (...) {
+    return FILM_ERR_CUDA;
+  }
+}
+
+int film_get_option(film_handle* h, const char* name, int* value) {
+  if (!h || !name || !value) return FILM_ERR_ARG;
+  if (!strcmp(name, "onepass_mask")) *value = (int)h->onepass_mask;
+  else if (!strcmp(name, "onepass_default")) *value = (int)kDefaultOnepassMask;
+  else if (!strcmp(name, "conv3x3_halo")) *value = h->conv3x3_halo;
+  else if (!strcmp(name, "conv3x3_2cta")) *value = h->conv3x3_2cta;
+  else if (!strcmp(name, "keep_debug")) *value = h->keep_debug;
+  else return FILM_ERR_ARG;
   return FILM_OK;
 }
 
@@ -1227,9 +1316,8 @@ int film_synchronize(film_handle* h) {
     FILM_CUDA(cudaSetDevice(h->device));
     FILM_CUDA(cudaStreamSynchronize(h->stream));
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 extern "C++" {
@@ -1363,9 +1451,8 @@ int film_interpolate(film_handle* h, const float* x0, const float* x1, const flo
     }
     fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1, int B, int H, int W,
@@ -1394,9 +1481,8 @@ int film_interpolate_device(film_handle* h, const float* d_x0, const float* d_x1
     fill_profile(h, P, -1.f, 0.f, 0.f);
     h->dev_events_valid = true;
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, const float* dt, int H, int W, int align,
@@ -1453,9 +1539,8 @@ int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, con
       }
     fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W, int align,
@@ -1528,9 +1613,8 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
     fill_profile(h, P, t_net, t_h2d, t_d2h);
     h->prof.kernel_launches = (int64_t)P->ops.size() * (n - 2);
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 void* film_host_alloc(size_t bytes) {
@@ -1562,6 +1646,7 @@ int film_profile(film_handle* h, film_profile_t* out) {
 
 int film_op_table(film_handle* h, char* buf, int64_t buf_size, int64_t* needed) {
   if (!h || !h->last_plan) return FILM_ERR_ARG;
+  try {
   std::string out = "idx,category,name,ms,ref_flops,alg_bytes\n";
   Plan* P = h->last_plan;
   for (size_t i = 0; i < P->ops.size(); ++i) {
@@ -1577,6 +1662,8 @@ int film_op_table(film_handle* h, char* buf, int64_t buf_size, int64_t* needed) 
     buf[n] = 0;
   }
   return FILM_OK;
+  }
+  FILM_CATCH_ALL(h)
 }
 
 int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count) {
@@ -1603,9 +1690,8 @@ int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count
       FILM_CUDA(e);
     }
     return FILM_OK;
-  } catch (const Error& e) {
-    return fail(h, e);
   }
+  FILM_CATCH_ALL(h)
 }
 
 }  // extern "C"

@@ -92,6 +92,20 @@ __device__ __forceinline__ uint64_t make_desc_kc(uint32_t saddr) {
   return d;
 }
 
+// Position in an mbarrier ring whose depth is a RUNTIME value: stage index + phase bit, advanced by
+// compare-and-wrap.  (`i % depth`, `(i / depth) & 1` compile to a ~25-instruction I2F / MUFU.RCP / F2I
+// sequence per use -- measurable in the per-tap issue path of the producer and MMA warps.)
+struct RingPos {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int depth) {
+    if (++stage == depth) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
 // K-major swizzled descriptor with an explicit stride between 8-row groups.  The hardware applies the
 // swizzle XOR on ABSOLUTE smem address bits (7..9 -> 4..6; 7..8 -> 4..5 for SWIZZLE_64B) and base_offset stays
 // 0: measured on B200 with tools/ubench/desc_offset_test.cu -- the start address may sit at any row inside

@@ -218,6 +218,20 @@ class Interpolator:
     def set_option(self, name: str, value: int) -> None:
         self._check(self._lib.film_set_option(self._handle, name.encode(), int(value)))
 
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        self._check(self._lib.film_get_option(self._handle, name.encode(), C.byref(v)))
+        return int(v.value)
+
+    def stage_names(self) -> List[str]:
+        """Stages of the precision plan; index = bit in the "onepass_mask" option."""
+        out = []
+        for i in range(self._lib.film_stage_count()):
+            buf = C.create_string_buffer(32)
+            self._lib.film_stage_name(i, buf, 32)
+            out.append(buf.value.decode())
+        return out
+
     def clear_cache(self) -> None:
         """Drops every cached per-shape plan (CUDA graph + activation arena) of this engine; the next call of a
         shape rebuilds it. For services that see many resolutions: plans are never evicted otherwise."""

@@ -68,7 +68,7 @@ typedef struct film_profile_t {
   double last_h2d_ms;         /* host->device copy time of the last host-pointer call     */
   double last_d2h_ms;         /* device->host copy time of the last host-pointer call     */
   double conv_flops;          /* reference-graph conv FLOPs of the last call (2*MAC)      */
-  double mma_flops;           /* tensor-core FLOPs actually issued (3 bf16 passes, padded K) */
+  double mma_flops;           /* tensor-core FLOPs actually issued (1 or 3 passes per stage, padded K) */
   double warp_bytes;          /* algorithmic bytes of the warp-gather kernels (rd+wr)      */
   int64_t kernel_launches;    /* kernels launched (or graph nodes replayed) by the last call */
   int64_t arena_bytes;        /* device memory held by the plan used by the last call     */
@@ -128,7 +128,8 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   1 = fp32 CUDA-core validation kernels (debug only; used by the
  *                       tests to cross-check the tensor-core path on the device)
  *   "use_graph"   : 1 = capture each shape's schedule in a CUDA graph (default), 0 = eager
- *   "keep_debug"  : 1 = keep intermediate tensors readable through film_debug_read
+ *   "keep_debug"  : 1 = keep every intermediate tensor alive (no arena reuse) so that film_debug_read can
+ *                   return it after the call; 0 (default) = activation buffers are recycled inside a plan
  *   "time_ops"    : 1 = run eagerly with one CUDA-event pair per kernel (see film_op_table)
  *   "conv3x3_v2"  : 1 = persistent tap-reuse kernel for 3x3 convs (default), 0 = generic kernel
  *   "conv3x3_2cta": 1 = CTA-pair (tcgen05 cta_group::2, M = 256) kernel for the streamed-weight 3x3
@@ -142,7 +143,18 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   after draining the handle's stream.  Plans are cached per shape and never evicted
  *                   otherwise, except that a shape whose arena cannot be allocated triggers one
  *                   drop-and-retry before FILM_ERR_CUDA is returned. */
+/*   "onepass_mask": precision plan -- bit s selects the single-pass product (A_hi x W_hi, fp16 operands, fp32
+ *                   accumulate) for stage s (film_stage_count / film_stage_name); every other conv runs the
+ *                   three-pass split product.  The default is the measured plan of DESIGN.md section 3;
+ *                   0 = every conv three-pass (fp32-grade).  "onepass_default" (any value) restores it. */
 FILM_API int film_set_option(film_handle* h, const char* name, int value);
+/* Reads back an integer option ("onepass_mask", "onepass_default", "conv3x3_halo", "conv3x3_2cta", "keep_debug"). */
+FILM_API int film_get_option(film_handle* h, const char* name, int* value);
+
+/* Stages of the precision plan: film_stage_count() names ("fe_i0_k01", "flow_L3", "fus2_c1", ...), index =
+ * bit position in "onepass_mask".  film_stage_name copies the NUL-terminated name into buf. */
+FILM_API int film_stage_count(void);
+FILM_API int film_stage_name(int stage, char* buf, int buf_size);
 
 /* Debug/parity hook: copies an intermediate tensor of the LAST call to host as float32
  * NHWC. `name` is e.g. "feat0/3" (feature pyramid of image 0, level 3), "flow_fwd/0",
@@ -158,7 +170,7 @@ FILM_API int film_op_table(film_handle* h, char* buf, int64_t buf_size, int64_t*
 
 FILM_API const char* film_last_error(film_handle* h);
 
-/* Version / build info string: "film_b200 <ver> sm_100a split=bf16x2 mma=kind::f16 3-pass". */
+/* Version / build info string: "film_b200 <ver> sm_100a split=fp16x2 mma=...". */
 FILM_API const char* film_version(void);
 
 #ifdef __cplusplus
