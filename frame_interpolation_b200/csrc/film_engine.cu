@@ -455,6 +455,7 @@ struct DebugTensor {
   const void* p1;
   int64_t npix;
   int C, c_off, Cn;
+  bool recycled = false;  // the buffer is reused later in the same plan (readable only with keep_debug = 1)
 };
 
 struct Plan {
@@ -498,25 +499,54 @@ struct Plan {
   cudaGraphExec_t graph = nullptr;
   double conv_flops = 0, mma_flops = 0, warp_bytes = 0;
 
+  // Activation arena with liveness-based reuse.  The schedule is built in execution order and replayed on ONE
+  // stream (or as the graph captured from it), so a buffer released at build position i may back any buffer
+  // allocated at a position >= i: release() returns a block to the pool, alloc() takes the best-fitting free
+  // block (at most 2x the request) before it asks the driver.  `pinned` buffers (network inputs/outputs, flows,
+  // tensors whose zero-initialised padding channels are never rewritten) are never recycled.  Reuse is off
+  // when intermediates must stay readable (keep_debug) or when branches run on concurrent streams (use_lanes).
+  bool reuse = true;
+  std::map<void*, int64_t> block_bytes;
+  std::multimap<int64_t, void*> free_blocks;
   template <class T>
-  T* alloc(int64_t count) {
+  T* alloc(int64_t count, bool pinned = false) {
+    const int64_t bytes = std::max<int64_t>(count * (int64_t)sizeof(T), 256);
+    if (reuse && !pinned) {
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= 2 * bytes) {
+        void* p = it->second;
+        free_blocks.erase(it);
+        return (T*)p;
+      }
+    }
     void* p;
-    const int64_t bytes = count * (int64_t)sizeof(T);
-    FILM_CUDA(cudaMalloc(&p, bytes > 0 ? bytes : 16));
-    FILM_CUDA(cudaMemset(p, 0, bytes > 0 ? bytes : 16));
+    FILM_CUDA(cudaMalloc(&p, bytes));
     allocs.push_back(p);
+    FILM_CUDA(cudaMemset(p, 0, bytes));
     arena_bytes += bytes;
+    if (!pinned) block_bytes[p] = bytes;
     return (T*)p;
   }
-  SplitBuf* split(int B, int H_, int W_, int C) {
+  // the buffer's last reader has been added to the schedule
+  void release(void* p) {
+    if (!reuse || !p) return;
+    auto it = block_bytes.find(p);
+    if (it != block_bytes.end()) free_blocks.insert({it->second, p});
+  }
+  void release(const SplitBuf* s) {
+    if (!s) return;
+    release((void*)s->hi);
+    release((void*)s->lo);
+  }
+  SplitBuf* split(int B, int H_, int W_, int C, bool pinned = false) {
     bufs.emplace_back(new SplitBuf);
     SplitBuf* s = bufs.back().get();
     s->B = B;
     s->H = H_;
     s->W = W_;
     s->C = C;
-    s->hi = alloc<sp_t>((int64_t)B * H_ * W_ * C);
-    s->lo = alloc<sp_t>((int64_t)B * H_ * W_ * C);
+    s->hi = alloc<sp_t>((int64_t)B * H_ * W_ * C, pinned);
+    s->lo = alloc<sp_t>((int64_t)B * H_ * W_ * C, pinned);
     return s;
   }
   std::vector<std::unique_ptr<SplitBuf>> bufs;
@@ -543,11 +573,14 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 // Adds one conv call site to the plan.  The GEMM-M grid is the grid of sources[0].
 static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
                        const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
-                       int stage, int sy = 1, int sx = 1, int oy = 0, int ox = 0, const SplitBuf* pool_out = nullptr,
-                       bool no_op = false) {
+                       int stage, int consumer, int sy = 1, int sx = 1, int oy = 0, int ox = 0,
+                       const SplitBuf* pool_out = nullptr, bool no_op = false) {
+  // `stage`: precision-plan stage of this conv.  `consumer`: stage of the ONLY reader of the destination when that
+  // reader is a conv (ST_NONE otherwise): a single-pass reader never touches the lo plane, so it is not written.
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
   cp.passes = (stage >= 0 && P.conv_impl == 0 && ((P.onepass_mask >> stage) & 1u)) ? 1 : 3;
+  cp.out_lo_skip = (consumer >= 0 && P.conv_impl == 0 && !pool_out && ((P.onepass_mask >> consumer) & 1u)) ? 1 : 0;
   const SplitBuf* s0 = sources[0].buf;
   cp.nsrc = (int)sources.size();
   if (cp.nsrc != (int)pc.src_chunks.size()) throw Error{FILM_ERR_WEIGHTS, "source count mismatch"};
@@ -689,10 +722,11 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
                                         int conv3x3_v2, int num_sms, int conv3x3_2cta, int conv3x3_halo,
-                                        uint32_t onepass_mask) {
+                                        uint32_t onepass_mask, bool use_lanes) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
   P.onepass_mask = onepass_mask;
+  P.reuse = !keep_debug && !use_lanes;
   P.h = h;
   P.w = w;
   P.conv_impl = conv_impl;
@@ -722,13 +756,13 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   }
   if (Hs[kLevels - 2] < 2 || Ws[kLevels - 2] < 2) throw Error{FILM_ERR_ARG, "frame too small"};
 
-  P.xin = P.alloc<float>((int64_t)2 * h * w * 3);
-  P.xout = P.alloc<float>((int64_t)h * w * 3);
+  P.xin = P.alloc<float>((int64_t)2 * h * w * 3, true);
+  P.xout = P.alloc<float>((int64_t)h * w * 3, true);
   Plan* pp = &P;
 
   // ---- image pyramids (util.py:23-45), both images batched: img[l] = [2][H_l][W_l][3]
   float* img[kLevels];
-  for (int l = 0; l < kLevels; ++l) img[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 3);
+  for (int l = 0; l < kLevels; ++l) img[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 3, true);
   for (int k = 0; k < 2; ++k) {
     float* dst = img[0] + (int64_t)k * P.H * P.W * 3;
     const float* src = P.xin + (int64_t)k * h * w * 3;
@@ -764,20 +798,20 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         // split tensor (3 real channels), K = 9 taps x one 32-channel block
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
-        SplitBuf* im32 = P.split(2, hh, ww, 32);
+        SplitBuf* im32 = P.split(2, hh, ww, 32, true);  // channels 8..31 stay zero: never recycled
         P.add_op(2, "fe_split32@L" + std::to_string(r),
                  [=](cudaStream_t st) { return launch_image_to_split32(im, 2, hh, ww, im32->hi, im32->lo, st); }, 0,
                  2.0 * hh * ww * (12 + 32.0));
-        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe0_3x3, {{im32, 0}}, 1, t1, 0, fe_stage(i, 0));
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe0_3x3, {{im32, 0}}, 1, t1, 0, fe_stage(i, 0), fe_stage(i, 1));
       } else if (j == 0 && P.conv_impl == 0) {
         // generic-kernel variant: im2col-lite (27 -> 32 channels) + a 1x1 conv, K = 32
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
-        SplitBuf* col = P.split(2, hh, ww, 32);
+        SplitBuf* col = P.split(2, hh, ww, 32, true);
         P.add_op(2, "fe_im2col@L" + std::to_string(r),
                  [=](cudaStream_t st) { return launch_im2col3x3(im, 2, hh, ww, col->hi, col->lo, st); }, 0,
                  2.0 * hh * ww * (12 + 128.0));
-        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe[0], {{col, 0}}, 1, t1, 0, fe_stage(i, 0));
+        add_conv(P, "fe_conv0@L" + std::to_string(r), 27.0 * 64, M.fe[0], {{col, 0}}, 1, t1, 0, fe_stage(i, 0), fe_stage(i, 1));
       } else if (j == 0) {
         const float* im = img[i];
         const int hh = Hs[r], ww = Ws[r];
@@ -788,7 +822,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
                  2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 + 64) * 4.0);
       } else {
         add_conv(P, "fe_conv" + std::to_string(2 * j) + "@L" + std::to_string(r), 9.0 * (c / 2) * c, M.fe[2 * j],
-                 {{pooled, 0}}, 1, t1, 0, fe_stage(i, 2 * j));
+                 {{pooled, 0}}, 1, t1, 0, fe_stage(i, 2 * j), fe_stage(i, 2 * j + 1));
+        P.release(pooled);  // consumed by this conv only
       }
       // second conv of the pair writes straight into the cascaded feature tensor slice
       // (replaces the tf.concat at feature_extractor.py:191)
@@ -796,7 +831,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       const bool fuse_pool = (j < depth - 1) && P.conv_impl == 0 && P.conv3x3_v2;
       if (j < depth - 1) pool_target = P.split(2, Hs[r + 1], Ws[r + 1], c);
       add_conv(P, "fe_conv" + std::to_string(2 * j + 1) + "@L" + std::to_string(r), 9.0 * c * c, M.fe[2 * j + 1],
-               {{t1, 0}}, 1, feat[r], slice_off[j], fe_stage(i, 2 * j + 1), 1, 1, 0, 0, fuse_pool ? pool_target : nullptr);
+               {{t1, 0}}, 1, feat[r], slice_off[j], fe_stage(i, 2 * j + 1), ST_NONE, 1, 1, 0, 0,
+               fuse_pool ? pool_target : nullptr);
+      P.release(t1);
       tok_feat[i][j] = P.new_token();
       P.signal_last(tok_feat[i][j]);
       if (fuse_pool) {
@@ -824,8 +861,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   float* v[kLevels];
   float* res[kLevels];
   for (int l = 0; l < kLevels; ++l) {
-    v[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
-    res[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2);
+    v[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2, true);
+    res[l] = P.alloc<float>((int64_t)2 * Hs[l] * Ws[l] * 2, true);
   }
   P.cur_lane = Plan::kNumLanes - 1;  // flow + fusion tail lane
   for (int l = kLevels - 1; l >= 0; --l) {
@@ -855,20 +892,33 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       const SplitBuf* f = feat[l];
       const int hc = Hs[l + 1], wc = Ws[l + 1];
       float* vu = vup;
+      // the warped features feed flow_conv0 of this level only: a single-pass consumer reads hi planes alone
+      const bool hi_only = P.conv_impl == 0 && ((P.onepass_mask >> (ST_FLOW_L0 + l)) & 1u);
+      const double wbytes = 2.0 * hh * ww * (double)C * (hi_only ? 4.0 : 8.0);
       P.add_op(1, "flow_warp@L" + std::to_string(l), [=](cudaStream_t st) {
-        return launch_flow_warp(vprev, hc, wc, f->hi, f->lo, hh, ww, C, vu, warped->hi, warped->lo, st);
-      }, 0, 2.0 * hh * ww * (double)C * 8.0);
-      P.warp_bytes += 2.0 * hh * ww * (double)C * 8.0;
+        return launch_flow_warp(vprev, hc, wc, f->hi, f->lo, hh, ww, C, vu, warped->hi, warped->lo, hi_only, st);
+      }, 0, wbytes);
+      P.warp_bytes += wbytes;
       second = warped;
+      // parity hooks: the flow-stage warp output (d = 0: features of image 1 warped by the forward flow) and the
+      // upsampled flow it was gathered with
+      for (int d = 0; d < 2; ++d) {
+        P.debug["flow_warped" + std::to_string(d) + "/" + std::to_string(l)] =
+            DebugTensor{true, warped->hi + (int64_t)d * hh * ww * C, warped->lo + (int64_t)d * hh * ww * C, (int64_t)hh * ww,
+                        C, 0, C};
+        P.debug["flow_vup" + std::to_string(d) + "/" + std::to_string(l)] =
+            DebugTensor{false, vup + (int64_t)d * hh * ww * 2, nullptr, (int64_t)hh * ww, 2, 0, 2};
+      }
     }
     const int cpad = round_up(nf, nf < kChunk ? 32 : kChunk);
     SplitBuf* c0 = P.split(2, hh, ww, cpad);
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);
     const std::string lt = "@L" + std::to_string(l);
-    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0, ST_FLOW_L0 + l);
-    add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l);
-    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0, ST_FLOW_L0 + l,
+             ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l, ST_NONE);
     if (P.conv_impl == 1) {
       // CUDA-core validation path keeps the standalone fp32 head kernel
       const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
@@ -881,7 +931,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     } else {
       // conv_3 (1x1, nf -> nf/2) on the tensor cores; conv_4 + residual add in its epilogue
       const size_t ci = add_conv(P, "flow_head" + lt, 1.0 * nf * (nf / 2) + (nf / 2) * 2.0, M.flow_c3[p], {{c2, 0}}, 1,
-                                 nullptr, 0, ST_NONE);
+                                 nullptr, 0, ST_NONE, ST_NONE);
       ConvProblem& hp = P.h_probs[ci];
       hp.epi_mode = 1;
       hp.head_w4 = M.flow_w4[p];
@@ -890,6 +940,13 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       hp.head_res = res[l];
       hp.head_v = v[l];
     }
+    // this level's temporaries are dead; so are the feature levels the fusion stage does not warp
+    P.release(second);
+    P.release(vup);
+    P.release(c0);
+    P.release(c1);
+    P.release(c2);
+    if (l >= kFusionLevels) P.release(feat[l]);
     const int64_t np = (int64_t)hh * ww;
     P.debug["flow_fwd/" + std::to_string(l)] = DebugTensor{false, v[l], nullptr, np, 2, 0, 2};
     P.debug["flow_bwd/" + std::to_string(l)] = DebugTensor{false, v[l] + np * 2, nullptr, np, 2, 0, 2};
@@ -904,17 +961,22 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   for (int l = 0; l < kFusionLevels; ++l) {
     const int C = feat_channels(l), hh = Hs[l], ww = Ws[l];
     wf[l] = P.split(2, hh, ww, C);
-    side[l] = P.split(1, hh, ww, kChunk);
+    side[l] = P.split(1, hh, ww, kChunk, true);  // channels 16..63 stay zero: never recycled
     const float* vv = v[l];
     const float* im = img[l];
     const SplitBuf *f = feat[l], *o = wf[l], *sd = side[l];
+    // consumers of the warped level: fusion_conv1 of the level (fusion_up of level 3 for the coarsest one)
+    const int cons = l == kFusionLevels - 1 ? ST_FUS + 3 * (l - 1) : ST_FUS + 3 * l + 1;
+    const bool hi_only = P.conv_impl == 0 && ((P.onepass_mask >> cons) & 1u);
+    const double wbytes = 2.0 * hh * ww * (double)C * (hi_only ? 4.0 : 8.0);
     P.add_op(1, "fusion_warp@L" + std::to_string(l), [=](cudaStream_t st) {
-      return launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, st);
-    }, 0, 2.0 * hh * ww * (double)C * 8.0);
+      return launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, hi_only, st);
+    }, 0, wbytes);
     P.add_op(2, "fusion_side@L" + std::to_string(l), [=](cudaStream_t st) {
       return launch_fusion_side(vv, im, hh, ww, sd->hi, sd->lo, sd->C, st);
     });
-    P.warp_bytes += 2.0 * hh * ww * (double)(C + 3) * 8.0;
+    P.warp_bytes += wbytes + 2.0 * hh * ww * 3.0 * 8.0;
+    P.release(feat[l]);  // the fusion-stage warp is the last reader of the feature level
     P.debug["aligned_side/" + std::to_string(l)] =
         DebugTensor{true, sd->hi, sd->lo, (int64_t)hh * ww, sd->C, 0, 10};
     for (int k = 0; k < 2; ++k)
@@ -947,7 +1009,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       size_t first = 0;
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
-          const size_t ci = add_conv(P, "", 0, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i, 2, 2, py, px, nullptr, true);
+          const size_t ci = add_conv(P, "", 0, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i, ST_FUS + 3 * i + 1, 2, 2,
+                                     py, px, nullptr, true);
           if (py == 0 && px == 0) first = ci;
         }
       P.h_probs[first].group = 4;
@@ -960,13 +1023,21 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px)
           add_conv(P, "fusion_up" + std::to_string(py * 2 + px) + "@L" + std::to_string(i),
-                   4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i, 2, 2, py, px);
+                   4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i,
+                   ST_FUS + 3 * i + 1, 2, 2, py, px);
     }
     SplitBuf* f1 = P.split(1, hh, ww, cpad);
     SplitBuf* f2 = P.split(1, hh, ww, cpad);
     add_conv(P, "fusion_conv1@L" + std::to_string(i), 9.0 * M.fus_c1[i].cin_ref * nf, M.fus_c1[i],
-             {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0, ST_FUS + 3 * i + 1);
-    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0, ST_FUS + 3 * i + 2);
+             {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0, ST_FUS + 3 * i + 1,
+             ST_FUS + 3 * i + 2);
+    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0, ST_FUS + 3 * i + 2,
+             i > 0 ? ST_FUS + 3 * (i - 1) : ST_NONE);
+    if (i == kFusionLevels - 2) P.release(wf[i + 1]);   // the coarsest aligned level fed fusion_up only
+    else P.release(net);                                // previous level's output, consumed by fusion_up
+    P.release(wf[i]);
+    P.release(up);
+    P.release(f1);
     net = f2;
     P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
     P.debug["fusion_up/" + std::to_string(i)] = DebugTensor{true, up->hi, up->lo, (int64_t)hh * ww, up->C, 0, nf};
@@ -1009,6 +1080,12 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     P.conv_flops = 2.0 * (fe + fl + fu);
   }
 
+  if (P.reuse)
+    for (auto& kv : P.debug)
+      if (P.block_bytes.count((void*)kv.second.p0) ||
+          kv.first.compare(0, 4, "feat") == 0 || kv.first.compare(0, 6, "warped") == 0 ||
+          kv.first.compare(0, 11, "flow_warped") == 0 || kv.first.compare(0, 8, "flow_vup") == 0)
+        kv.second.recycled = true;  // (batch views point into the middle of a recycled block)
   FILM_CUDA(cudaMalloc(&P.d_probs, P.h_probs.size() * sizeof(ConvProblem)));
   P.allocs.push_back(P.d_probs);
   FILM_CUDA(cudaMemcpy(P.d_probs, P.h_probs.data(), P.h_probs.size() * sizeof(ConvProblem), cudaMemcpyHostToDevice));
@@ -1121,7 +1198,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   std::unique_ptr<Plan> p;
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask);
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0);
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1129,7 +1206,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     if (h->plans.empty()) throw;
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask);
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0);
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1673,6 +1750,9 @@ int film_debug_read(film_handle* h, const char* name, float* dst, int64_t* count
     auto it = h->last_plan->debug.find(name);
     if (it == h->last_plan->debug.end()) throw Error{FILM_ERR_ARG, std::string("unknown debug tensor ") + name};
     const DebugTensor& d = it->second;
+    if (d.recycled)
+      throw Error{FILM_ERR_ARG, std::string(name) + " lives in a recycled activation buffer: set option keep_debug = 1 "
+                                                    "before the call to read intermediates"};
     const int64_t n = d.npix * d.Cn;
     if (count) *count = n;
     if (!dst) return FILM_OK;

@@ -329,9 +329,30 @@ __device__ __forceinline__ void gather16(const sp_t* __restrict__ hi, const sp_t
   }
 }
 
+// hi-plane-only gather: for destinations whose only consumers are single-pass convs (they read the hi plane
+// alone, so the source is taken at hi precision too and the lo planes are neither read nor written)
+__device__ __forceinline__ void gather16_hi(const sp_t* __restrict__ hi, int W, int C, int c, const WarpTap& t,
+                                            float* out) {
+  const sp_t* h0 = hi + ((int64_t)t.y0 * W + t.x0) * C + c;
+  const int row = W * C;
+  float a[16], b[16], top[16];
+  load_unpack16_hi(h0, a);
+  load_unpack16_hi(h0 + C, b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) top[j] = t.ax * (b[j] - a[j]) + a[j];
+  load_unpack16_hi(h0 + row, a);
+  load_unpack16_hi(h0 + row + C, b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float bot = t.ax * (b[j] - a[j]) + a[j];
+    out[j] = t.ay * (bot - top[j]) + top[j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pyramid_flow_estimator.py:154-157  flow upsample (x2 magnitude) fused with the feature warp
 // ------------------------------------------------------------------------------------------
+template <bool kHiOnly>
 __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_prev, int Hc, int Wc,
                                                    const sp_t* __restrict__ feat_hi,
                                                    const sp_t* __restrict__ feat_lo, int H, int W, int C,
@@ -357,21 +378,28 @@ __global__ void __launch_bounds__(256) k_flow_warp(const float* __restrict__ v_p
   WarpTap t = warp_tap(y, x, f.x, f.y, H, W);
   const int64_t src_off = (int64_t)(1 - d) * H * W * C;
   float o[16];
-  gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
-  pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
+  if constexpr (kHiOnly) {
+    gather16_hi(feat_hi + src_off, W, C, c, t, o);
+    pack_store16_hi(o, warped_hi + p * C + c);
+  } else {
+    gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
+    pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
+  }
 }
 
 cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
                              const sp_t* feat_lo, int H, int W, int C, float* v_up,
-                             sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
+                             sp_t* warped_hi, sp_t* warped_lo, bool hi_only, cudaStream_t st) {
   dim3 grid((W + 7) / 8, (H + 7) / 8, 2 * (C / 64));
-  k_flow_warp<<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
+  if (hi_only) k_flow_warp<true><<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
+  else k_flow_warp<false><<<grid, 256, 0, st>>>(v_prev, Hc, Wc, feat_hi, feat_lo, H, W, C, v_up, warped_hi, warped_lo);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
 // interpolator.py:163-178  fusion-stage warps (flows scaled by 0.5)
 // ------------------------------------------------------------------------------------------
+template <bool kHiOnly>
 __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v,
                                                      const sp_t* __restrict__ feat_hi,
                                                      const sp_t* __restrict__ feat_lo, int H, int W,
@@ -389,14 +417,20 @@ __global__ void __launch_bounds__(256) k_fusion_warp(const float* __restrict__ v
   WarpTap t = warp_tap(y, x, f.x * 0.5f, f.y * 0.5f, H, W);
   const int64_t src_off = (int64_t)k * H * W * C;
   float o[16];
-  gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
-  pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
+  if constexpr (kHiOnly) {
+    gather16_hi(feat_hi + src_off, W, C, c, t, o);
+    pack_store16_hi(o, warped_hi + p * C + c);
+  } else {
+    gather16(feat_hi + src_off, feat_lo + src_off, W, C, c, t, o);
+    pack_store16(o, warped_hi + p * C + c, warped_lo + p * C + c);
+  }
 }
 
 cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
-                               int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st) {
+                               int W, int C, sp_t* warped_hi, sp_t* warped_lo, bool hi_only, cudaStream_t st) {
   dim3 grid((W + 7) / 8, (H + 7) / 8, 2 * (C / 64));
-  k_fusion_warp<<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
+  if (hi_only) k_fusion_warp<true><<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
+  else k_fusion_warp<false><<<grid, 256, 0, st>>>(v, feat_hi, feat_lo, H, W, C, warped_hi, warped_lo);
   return cudaGetLastError();
 }
 

@@ -31,7 +31,9 @@ cudaError_t launch_act_pool(const sp_t* in_hi, const sp_t* in_lo, int in_C, int 
 // warped[d] = warp(feat[1-d], v_up[d]).  feat/warped are [2][H][W][C] split tensors.
 cudaError_t launch_flow_warp(const float* v_prev, int Hc, int Wc, const sp_t* feat_hi,
                              const sp_t* feat_lo, int H, int W, int C, float* v_up,
-                             sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st);
+                             sp_t* warped_hi, sp_t* warped_lo, bool hi_only, cudaStream_t st);
+// hi_only (both gathers): the destination's only consumers are single-pass convs -> read and write the hi
+// planes alone (half the bytes; the lo planes of the destination are left untouched and never read)
 
 // pyramid_flow_estimator.py:77-83,96-97 (conv_3: 1x1 nf->nf/2 LReLU, conv_4: 1x1 ->2 linear)
 // fused with :161 (v = v_residual + v).  x: [2][H][W][Cx] split (first nf channels real).
@@ -43,7 +45,7 @@ cudaError_t launch_flow_head(const sp_t* x_hi, const sp_t* x_lo, int Cx, int nf,
 // warped[k] = warp(feat[k], 0.5 * v[1-k])   (k = 0: image 0 by backward flow, k = 1: image 1
 // by forward flow; v[0] = forward flow, v[1] = backward flow).
 cudaError_t launch_fusion_warp(const float* v, const sp_t* feat_hi, const sp_t* feat_lo, int H,
-                               int W, int C, sp_t* warped_hi, sp_t* warped_lo, cudaStream_t st);
+                               int W, int C, sp_t* warped_hi, sp_t* warped_lo, bool hi_only, cudaStream_t st);
 // side tensor [1][H][W][side_C] split: ch 0-2 warp(img0, .5*bwd), 3-5 warp(img1, .5*fwd),
 // 6-7 .5*bwd, 8-9 .5*fwd, 10-15 zero.
 cudaError_t launch_fusion_side(const float* v, const float* img, int H, int W, sp_t* side_hi,

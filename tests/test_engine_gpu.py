@@ -1,6 +1,9 @@
 """Parity tests proper: the CUDA engine (through the C ABI / Interpolator drop-in) against the
 CPU oracle and the committed golden vectors. Tolerance: north_star's max-abs <= 1e-3 on the
-fp32 output (we assert 2e-4, the engine's split-bf16 3-pass MMA measures ~5e-5)."""
+fp32 output. Two bars below it:
+  PLAN  (4e-4): the default precision plan (single-pass fp16 MMAs on the stages the measured study allows,
+                profiles/r2_precision_study_1080p.md: 2.4e-4 at 1080p, >= 3x under the contract on average);
+  TIGHT (1e-4): every conv on the three-pass split product (option onepass_mask = 0): measures 3e-5 .. 7e-5."""
 import ast
 import glob
 import os
@@ -13,7 +16,8 @@ from frame_interpolation_b200 import spec, synthetic, weights
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3          # the contract (BASELINE.json north_star)
-TIGHT = 2e-4        # what we actually hold ourselves to
+PLAN = 4e-4         # default precision plan
+TIGHT = 1e-4        # all-three-pass engine (onepass_mask = 0)
 DT = np.full((1,), 0.5, np.float32)
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
 
@@ -23,6 +27,16 @@ def engine(synthetic_weights):
     from frame_interpolation_b200.interpolator import Interpolator
     path, _ = synthetic_weights
     eng = Interpolator(path, align=64)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def engine3(synthetic_weights):
+    """Engine with every conv on the three-pass split product (fp32-grade)."""
+    from frame_interpolation_b200.interpolator import Interpolator
+    eng = Interpolator(synthetic_weights[0], align=64)
+    eng.set_option("onepass_mask", 0)
     yield eng
     eng.close()
 
@@ -50,25 +64,37 @@ def test_engine_matches_golden_vectors(path, synthetic_weights):
     eng = Interpolator(synthetic_weights[0], align=c["align"], block_shape=c["block"])
     out = eng(x0, x1, DT)
     assert out.dtype == np.float32 and out.shape == z["image"].shape
-    assert np.abs(out - z["image"]).max() < TIGHT
+    assert np.abs(out - z["image"]).max() < PLAN
+    eng.set_option("onepass_mask", 0)
+    assert np.abs(eng(x0, x1, DT) - z["image"]).max() < TIGHT
     eng.close()
 
 
 @pytest.mark.parametrize("h,w,seed", [(64, 64, 0), (128, 192, 1), (256, 256, 2), (192, 320, 3), (100, 150, 4), (65, 129, 5)])
-def test_engine_matches_oracle(engine, oracle, h, w, seed):
+def test_engine_matches_oracle(engine, engine3, oracle, h, w, seed):
     x0, x1 = synthetic.frame_pair(h, w, seed=seed, n_waves=8)
-    out = engine(x0, x1, DT)
     ref = oracle(x0, x1, DT)
-    err = np.abs(out.astype(np.float64) - ref).max()
-    assert out.shape == ref.shape == (1, h, w, 3)
-    assert err < TIGHT, err
-    assert psnr(out, ref) > 80.0                     # i.e. PSNR delta vs the reference << 0.01 dB
+    for eng, tol in ((engine, PLAN), (engine3, TIGHT)):
+        out = eng(x0, x1, DT)
+        err = np.abs(out.astype(np.float64) - ref).max()
+        assert out.shape == ref.shape == (1, h, w, 3)
+        assert err < tol, err
+        assert psnr(out, ref) > 80.0                 # i.e. PSNR delta vs the reference << 0.01 dB
 
 
-def test_intermediate_tensors_match_oracle(engine, oracle):
-    """Stage-by-stage parity: feature pyramid, residual flows, flows, warped pyramids."""
+def test_intermediate_tensors_match_oracle(engine3, oracle):
+    """Stage-by-stage parity (three-pass engine): feature pyramid, residual flows, flows, warped pyramids."""
+    engine = engine3
     x0, x1 = synthetic.frame_pair(128, 128, seed=9, n_waves=8)
+    engine.set_option("keep_debug", 1)        # intermediates live in recycled arena blocks otherwise
     engine.interpolate(x0, x1, DT)
+    engine.set_option("keep_debug", 0)
+    with pytest.raises(AssertionError, match="keep_debug"):
+        engine.interpolate(x0, x1, DT)        # plan without keep_debug: intermediates are recycled ...
+        engine.debug_read("feat0/0")          # ... and reading one is refused, not silently stale
+    engine.set_option("keep_debug", 1)
+    engine.interpolate(x0, x1, DT)
+    engine.set_option("keep_debug", 0)
     aux = {}
     oracle.interpolate(x0, x1, DT, aux)
 
@@ -81,12 +107,13 @@ def test_intermediate_tensors_match_oracle(engine, oracle):
         assert np.abs(engine.debug_read(f"res_fwd/{l}") - nhwc(aux["forward_residual_flow_pyramid"][l])).max() < 5e-4
         assert np.abs(engine.debug_read(f"res_bwd/{l}") - nhwc(aux["backward_residual_flow_pyramid"][l])).max() < 5e-4
     for l in range(spec.FUSION_PYRAMID_LEVELS):
-        assert np.abs(engine.debug_read(f"flow_fwd/{l}") - nhwc(aux["forward_flow_pyramid"][l])).max() < 5e-3
-        assert np.abs(engine.debug_read(f"flow_bwd/{l}") - nhwc(aux["backward_flow_pyramid"][l])).max() < 5e-3
+        assert np.abs(engine.debug_read(f"flow_fwd/{l}") - nhwc(aux["forward_flow_pyramid"][l])).max() < 5e-4
+        assert np.abs(engine.debug_read(f"flow_bwd/{l}") - nhwc(aux["backward_flow_pyramid"][l])).max() < 5e-4
         C = spec.feature_channels(l)
         al = aux["aligned_pyramid"][l]
-        assert np.abs(engine.debug_read(f"warped0/{l}") - nhwc(al[:, 3:3 + C])).max() < 5e-3
-        assert np.abs(engine.debug_read(f"warped1/{l}") - nhwc(al[:, 6 + C:6 + 2 * C])).max() < 5e-3
+        scale = max(1.0, float(al.abs().max()))
+        assert np.abs(engine.debug_read(f"warped0/{l}") - nhwc(al[:, 3:3 + C])).max() < 5e-4 * scale
+        assert np.abs(engine.debug_read(f"warped1/{l}") - nhwc(al[:, 6 + C:6 + 2 * C])).max() < 5e-4 * scale
 
 
 def test_tensor_core_path_agrees_with_cuda_core_validation_path(synthetic_weights):
@@ -94,6 +121,7 @@ def test_tensor_core_path_agrees_with_cuda_core_validation_path(synthetic_weight
     from frame_interpolation_b200.interpolator import Interpolator
     x0, x1 = synthetic.frame_pair(128, 192, seed=11, n_waves=8)
     a = Interpolator(synthetic_weights[0], align=64)
+    a.set_option("onepass_mask", 0)
     b = Interpolator(synthetic_weights[0], align=64)
     b.set_option("conv_impl", 1)
     oa, ob = a(x0, x1, DT), b(x0, x1, DT)
@@ -117,7 +145,7 @@ def test_batch_of_pairs(engine, oracle):
     assert out.shape == (3, 64, 128, 3)
     for i in range(3):
         np.testing.assert_array_equal(out[i:i + 1], engine(x0[i:i + 1], x1[i:i + 1], DT))
-    assert np.abs(out - oracle(x0, x1, np.full((3,), 0.5, np.float32))).max() < TIGHT
+    assert np.abs(out - oracle(x0, x1, np.full((3,), 0.5, np.float32))).max() < PLAN
 
 
 def test_tiled_path_matches_oracle_tiled_path_and_per_tile_calls(synthetic_weights):
@@ -128,7 +156,7 @@ def test_tiled_path_matches_oracle_tiled_path_and_per_tile_calls(synthetic_weigh
     out = eng(x0, x1, DT)
     ref = OracleInterpolator(synthetic_weights[1], align=64, block_shape=[2, 2])(x0, x1, DT)
     assert out.shape == (1, 200, 300, 3)
-    assert np.abs(out - ref).max() < TIGHT
+    assert np.abs(out - ref).max() < PLAN
     # seams are part of the reference behaviour: every tile equals an independent call on that tile
     single = Interpolator(synthetic_weights[0], align=64)
     p0, p1 = image_to_patches(x0, [2, 2]), image_to_patches(x1, [2, 2])
@@ -152,8 +180,10 @@ def test_argument_errors_mirror_the_reference(engine, synthetic_weights):
     noalign = Interpolator(synthetic_weights[0], align=None)
     assert noalign(x0, x1, DT).shape == (1, 64, 64, 3)            # already 64-aligned: fine without padding
     x0b, x1b = synthetic.frame_pair(70, 64, seed=0, n_waves=4)
-    with pytest.raises(AssertionError):
-        noalign(x0b, x1b, DT)                                     # the reference graph fails on unaligned sizes too
+    # The reference graph accepts unaligned sizes (VALID pooling floors); this engine implements the 64-aligned
+    # case only and says so with FILM_ERR_UNSUPPORTED -- a capability limit, not an argument error
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        noalign(x0b, x1b, DT)
     noalign.close()
     with pytest.raises(RuntimeError, match="weight"):
         Interpolator("/nonexistent/weights.filmw")
@@ -213,8 +243,11 @@ def test_full_size_1080p_parity_and_properties(synthetic_weights):
     ref = OracleInterpolator(synthetic_weights[1], align=64)(x0, x1, DT)
     err = np.abs(out.astype(np.float64) - ref).max()
     assert err < TOL, err
-    assert err < 5e-4, err
+    assert err < PLAN, err                 # default precision plan: 2.4e-4 measured
     assert psnr(out, ref) > 80.0
+    eng.set_option("onepass_mask", 0)      # every conv three-pass: 7e-5 measured
+    err3 = np.abs(eng(x0, x1, DT).astype(np.float64) - ref).max()
+    assert err3 < 1.5e-4, err3
     eng.close()
 
 
@@ -259,7 +292,7 @@ def test_cli_end_to_end(tmp_path, synthetic_weights):
 
 
 @pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0),
-                                          ("conv3x3_halo", 0), ("conv3x3_halo", 1)])
+                                          ("conv3x3_halo", 0), ("conv3x3_halo", 1), ("conv3x3_halo", 2), ("conv3x3_halo", 3)])
 def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers, wide-halo boxes off /
     pair-only; the default is wide halo in both persistent kernels) meets the same bar."""
@@ -269,9 +302,14 @@ def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     eng = Interpolator(synthetic_weights[0], align=64)
     eng.set_option(option, value)
     out = eng(x0, x1, DT)
-    assert np.abs(out.astype(np.float64) - ref).max() < TIGHT
+    assert np.abs(out.astype(np.float64) - ref).max() < PLAN
     default = Interpolator(synthetic_weights[0], align=64)
-    assert np.abs(out - default(x0, x1, DT)).max() < 1e-4
+    assert np.abs(out - default(x0, x1, DT)).max() < 1e-4      # same precision plan, different kernels
+    for e in (eng, default):
+        e.set_option("onepass_mask", 0)
+    out3 = eng(x0, x1, DT)
+    assert np.abs(out3.astype(np.float64) - ref).max() < TIGHT
+    assert np.abs(out3 - default(x0, x1, DT)).max() < 5e-5
     eng.close()
     default.close()
 
@@ -309,6 +347,105 @@ def test_clear_cache_drops_plans_and_results_are_reproduced(synthetic_weights):
     a, b = eng(x0, x1, DT).copy(), eng(y0, y1, DT).copy()
     assert eng.profile()["arena_bytes"] > 0
     eng.clear_cache()
-    np.testing.assert_allclose(eng(y0, y1, DT), b, rtol=0, atol=1e-6)
-    np.testing.assert_allclose(eng(x0, x1, DT), a, rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(eng(y0, y1, DT), b)      # same shape -> same plan -> same bits
+    np.testing.assert_array_equal(eng(x0, x1, DT), a)
     eng.close()
+
+
+def _flow_bias_weights(tmp_path, base, bias_xy, tag):
+    """Synthetic weights whose flow predictors output a CONSTANT residual: conv_4 kernel = 0, bias = bias_xy.
+    The flow pyramid is then known in closed form (v_l = 2 * up(v_{l+1}) + b) and can be made as large as wanted."""
+    from frame_interpolation_b200 import weights as W
+    w = {k: np.array(v, copy=True) for k, v in base.items()}
+    for p in ("flow_predictor_0", "flow_predictor_1", "flow_predictor_2", "flow_predictor_shared"):
+        w[f"predict_flow/{p}/conv_4/kernel"][...] = 0.0
+        w[f"predict_flow/{p}/conv_4/bias"][...] = np.asarray(bias_xy, np.float32)
+    path = str(tmp_path / f"flowbias_{tag}.filmw")
+    W.save(path, w)
+    return path, w
+
+
+@pytest.mark.parametrize("bias_xy,tag", [((3.0, -2.0), "integer_landings"), ((2.75, 1.5), "twice_the_frame"),
+                                         ((-0.4375, 0.3125), "fractional_negative")])
+def test_warp_kernels_edge_cases(tmp_path, synthetic_weights, bias_xy, tag):
+    """The gather kernels against `dense_image_warp` (models/film_net/util.py:48-82 + the TFA 0.15 rule: per axis
+    floor = min(max(0, floor(q)), size - 2), alpha = clip(q - floor, 0, 1)) where a naive clamp would differ:
+    flows far larger than the frame (|v_0| = 127 * |b|: 381 px on a 128 x 192 frame), integer flows landing exactly
+    on pixels, on the border and on size - 1, negative coordinates; at every level, both stages (flow-stage warp by
+    the upsampled flow, fusion-stage warp by 0.5 * flow). The kernels are isolated from the convs by feeding the
+    ORACLE's warp with the engine's own features and flows."""
+    import torch
+    from frame_interpolation_b200.interpolator import Interpolator
+    from oracle import film_oracle as O
+    path, w = _flow_bias_weights(tmp_path, synthetic_weights[1], bias_xy, tag)
+    h, wd = 128, 192
+    x0, x1 = synthetic.frame_pair(h, wd, seed=31, n_waves=8)
+    eng = Interpolator(path, align=64)
+    eng.set_option("onepass_mask", 0)
+    eng.set_option("keep_debug", 1)
+    eng(x0, x1, DT)
+    sizes = spec.level_sizes(h, wd)
+
+    def t_nchw(flat, hh, ww, c):
+        return torch.from_numpy(flat.reshape(1, hh, ww, c)).permute(0, 3, 1, 2).contiguous()
+
+    # closed-form flow pyramid: v_6 = b, v_l = 2 * v_{l+1} + b  (bilinear upsampling of a constant is the constant)
+    v = np.asarray(bias_xy, np.float64)
+    expect = {}
+    for l in reversed(range(spec.PYRAMID_LEVELS)):
+        expect[l] = v.copy()
+        v = 2 * v + np.asarray(bias_xy, np.float64)
+    assert max(abs(expect[0])) > 30
+    for l in range(spec.PYRAMID_LEVELS):
+        hh, ww = sizes[l]
+        C = spec.feature_channels(l)
+        for name in (f"flow_fwd/{l}", f"flow_bwd/{l}"):
+            got = eng.debug_read(name).reshape(hh, ww, 2)
+            assert np.abs(got - expect[l].astype(np.float32)).max() <= 1e-5 * max(1.0, abs(expect[l]).max()), (name, tag)
+        feats = [t_nchw(eng.debug_read(f"feat{k}/{l}"), hh, ww, C) for k in range(2)]
+        fscale = max(1.0, float(max(f.abs().max() for f in feats)))
+        if l < spec.PYRAMID_LEVELS - 1:
+            # flow-stage warp: direction d warps the features of image 1 - d by the upsampled flow of direction d
+            for d in range(2):
+                vup = t_nchw(eng.debug_read(f"flow_vup{d}/{l}"), hh, ww, 2)
+                want = O.warp(feats[1 - d], vup)[0].permute(1, 2, 0).reshape(-1).numpy()
+                got = eng.debug_read(f"flow_warped{d}/{l}")
+                assert np.abs(got - want).max() <= 1e-5 * fscale, (l, d, tag)
+        if l < spec.FUSION_PYRAMID_LEVELS:
+            # fusion-stage warp: image k by 0.5 * flow of direction 1 - k (interpolator.py:163-178)
+            flows = [t_nchw(eng.debug_read(n), hh, ww, 2) for n in (f"flow_fwd/{l}", f"flow_bwd/{l}")]
+            for k in range(2):
+                want = O.warp(feats[k], 0.5 * flows[1 - k])[0].permute(1, 2, 0).reshape(-1).numpy()
+                got = eng.debug_read(f"warped{k}/{l}")
+                assert np.abs(got - want).max() <= 1e-5 * fscale, (l, k, tag)
+    # and the whole network still matches the oracle with these weights
+    ref = O.OracleInterpolator(w, align=64)(x0, x1, DT)
+    assert np.abs(eng(x0, x1, DT).astype(np.float64) - ref).max() < TIGHT
+    eng.close()
+
+
+@pytest.mark.timeout(900)
+def test_4k_tiled_2x2_at_real_tile_size(synthetic_weights):
+    """BASELINE.json configs[2] at its real size: 3840x2160, block 2x2 -> four 1080x1920 tiles, each padded on its own
+    to 1088x1920 (eval/interpolator.py:192-206). One tile is checked against the oracle, all four against independent
+    engine calls on the tile (seams are reference behaviour), and the stitch geometry against the tile order."""
+    import torch
+    from frame_interpolation_b200.interpolator import Interpolator, image_to_patches
+    from oracle.film_oracle import OracleInterpolator
+    x0, x1 = synthetic.frame_pair(2160, 3840, seed=5, n_waves=8)
+    eng = Interpolator(synthetic_weights[0], align=64, block_shape=[2, 2])
+    out = eng(x0, x1, DT)
+    assert out.shape == (1, 2160, 3840, 3) and np.isfinite(out).all()
+    single = Interpolator(synthetic_weights[0], align=64)
+    p0, p1 = image_to_patches(x0, [2, 2]), image_to_patches(x1, [2, 2])
+    for t in range(4):
+        r, c = divmod(t, 2)
+        np.testing.assert_array_equal(out[0, r * 1080:(r + 1) * 1080, c * 1920:(c + 1) * 1920],
+                                      single(p0[t][None], p1[t][None], DT)[0])
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    t = 3                                                       # bottom-right tile
+    ref = OracleInterpolator(synthetic_weights[1], align=64)(p0[t][None], p1[t][None], DT)
+    err = np.abs(out[0, 1080:, 1920:].astype(np.float64) - ref[0]).max()
+    assert err < PLAN, err
+    eng.close()
+    single.close()

@@ -20,6 +20,13 @@ def fake_engine(x0, x1, dt):
     return 0.5 * (x0 + x1) + 1e-3 * ramp
 
 
+def fake_engine_dev(x0, x1, out):
+    """Tensor-view form of `fake_engine` (the engine_dev interface of the device-resident path)."""
+    h, w, _ = x0.shape
+    ramp = torch.arange(h * w, dtype=torch.float32).view(h, w, 1)
+    out.copy_(0.5 * (x0 + x1) + 1e-3 * ramp)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -41,6 +48,12 @@ def _worker(rank, world, port, q):
     big1 = rng.random((1, 12, 18, 3), dtype=np.float32)
     res["tiled"] = parallel.interpolate_tiled(fake_engine, big0, big1, [3, 3])
     res["rec"] = np.stack(parallel.interpolate_recursively(fake_engine, a[0], b[0], 3))
+    # device-resident path (tensor views, in-place all-gather of the slot buffer), here on CPU tensors
+    ta, tb, t0, t1 = (torch.from_numpy(x) for x in (a, b, big0, big1))
+    res["pairs_dev"] = parallel.interpolate_pairs_device(fake_engine_dev, ta, tb).numpy()
+    res["tiled_dev"] = parallel.interpolate_tiled_device(fake_engine_dev, t0, t1, [3, 3]).numpy()
+    res["tiled_dev_4x4"] = parallel.interpolate_tiled_device(fake_engine_dev, ta[:1], tb[:1], [4, 4]).numpy()
+    res["rec_dev"] = parallel.interpolate_recursively_device(fake_engine_dev, ta[0], tb[0], 3).numpy()
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -86,6 +99,13 @@ def test_single_process_paths_match_serial():
     np.testing.assert_array_equal(parallel.interpolate_tiled(fake_engine, big0, big1, [3, 3]), tiled)
     np.testing.assert_array_equal(np.stack(parallel.interpolate_recursively(fake_engine, a[0], b[0], 3)), seq)
     assert seq.shape[0] == 2 ** 3 + 1
+    ta, tb, t0, t1 = (torch.from_numpy(x) for x in (a, b, big0, big1))
+    np.testing.assert_array_equal(parallel.interpolate_pairs_device(fake_engine_dev, ta, tb).numpy(), pairs)
+    np.testing.assert_array_equal(parallel.interpolate_tiled_device(fake_engine_dev, t0, t1, [3, 3]).numpy(), tiled)
+    np.testing.assert_array_equal(parallel.interpolate_recursively_device(fake_engine_dev, ta[0], tb[0], 3).numpy(), seq)
+    # strided tile views: a tile is a row-pitched window of the frame, never a copy
+    v = parallel.tile_view(t0, [3, 3], 4)
+    assert v.shape == (4, 6, 3) and v.stride(0) == 18 * 3 and v.data_ptr() == t0[0, 4, 6].data_ptr()
 
 
 @pytest.mark.timeout(180)
@@ -102,10 +122,18 @@ def test_world_size_2_gloo_bitwise_equals_serial():
         p.join(timeout=60)
         assert p.exitcode == 0
     pairs, tiled, seq = _serial_reference()
+    rng = np.random.default_rng(0)
+    a = rng.random((5, 8, 12, 3), dtype=np.float32)
+    b = rng.random((5, 8, 12, 3), dtype=np.float32)
+    tiled44 = parallel.interpolate_tiled(fake_engine, a[:1], b[:1], [4, 4])    # world 1: the serial tiled path
     for r in range(world):
         np.testing.assert_array_equal(got[r]["pairs"], pairs)
         np.testing.assert_array_equal(got[r]["tiled"], tiled)
         np.testing.assert_array_equal(got[r]["rec"], seq)
+        np.testing.assert_array_equal(got[r]["pairs_dev"], pairs)
+        np.testing.assert_array_equal(got[r]["tiled_dev"], tiled)
+        np.testing.assert_array_equal(got[r]["rec_dev"], seq)
+        np.testing.assert_array_equal(got[r]["tiled_dev_4x4"], tiled44)
     # local shares: rank 0 gets pairs [0,3), rank 1 gets [3,5)
     np.testing.assert_array_equal(got[0]["pairs_local"], pairs[:3])
     np.testing.assert_array_equal(got[1]["pairs_local"], pairs[3:])

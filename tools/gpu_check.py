@@ -28,6 +28,7 @@ eng = Interpolator(wpath, align=64)
 print(eng.version, flush=True)
 eng.set_option("conv_impl", 1 if a.impl == "simt" else 0)
 eng.set_option("use_graph", a.graph)
+eng.set_option("keep_debug", 1)
 t = time.time()
 out = eng.interpolate(x0, x1, dt)
 print(f"engine first call {time.time()-t:.3f}s  profile {eng.profile()}", flush=True)

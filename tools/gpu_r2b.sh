@@ -1,0 +1,31 @@
+#!/bin/bash
+# round 2, GPU call B: full parity suite, kernel-option A/B benches on one box, precision study (2 seeds),
+# the complete bench line (with the 4K / 8K / 720p workloads), ncu evidence.
+mkdir -p gpurun_out
+T=r2b
+timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
+tail -25 gpurun_out/${T}_pytest.log
+for cfg in "default" "FILM_HALO=3" "FILM_2CTA=2" "FILM_2CTA=0" "FILM_HALO=0"; do
+  name=$(echo $cfg | tr '=' '_')
+  if [ "$cfg" = "default" ]; then envs=""; else envs="$cfg"; fi
+  env $envs timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-workloads --op-table gpurun_out/${T}_ops_$name.csv > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_$name.json"))
+    print("$cfg", "ms/step %.3f" % d["ms_per_step"], "fps %.2f" % d["value"], "e2e %.2f" % d["e2e"]["value"], "frac %.3f" % d["roofline"]["frac"], "conv ms %.3f" % d["roofline"]["conv_kernel_ms_per_step"], "gather GB/s %.0f" % d["gather"]["achieved"], d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("$cfg failed", e)
+PY
+done
+timeout 1200 python tools/precision_study.py --height 1080 --width 1920 --seeds 0,1 --out gpurun_out/${T}_precision_1080p > gpurun_out/${T}_precision.log 2>&1; echo "study rc=$?"
+tail -3 gpurun_out/${T}_precision.log
+timeout 900 python bench.py --steps 20 --warmup 3 --op-table gpurun_out/${T}_ops.csv > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
+tail -c 2500 gpurun_out/${T}_bench.json; tail -5 gpurun_out/${T}_bench.err
+# ncu: launch list of one eager call (second call), light sections for every kernel, full set for the conv kernels and gathers
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python tools/profile_step.py 1 > gpurun_out/${T}_ncu_list.log 2>&1
+timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section SchedulerStats --clock-control none -s 140 -c 140 -f -o gpurun_out/${T}_all python tools/profile_step.py 1 > gpurun_out/${T}_ncu_all.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_tc2 -c 20 -f -o gpurun_out/${T}_pair python tools/profile_step.py 0 > gpurun_out/${T}_ncu_pair.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_conv3x3_tc<" -c 30 -f -o gpurun_out/${T}_single python tools/profile_step.py 0 > gpurun_out/${T}_ncu_single.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_flow_warp|k_fusion_warp|k_conv_tc" -c 24 -f -o gpurun_out/${T}_misc python tools/profile_step.py 0 > gpurun_out/${T}_ncu_misc.log 2>&1
+ls -la gpurun_out | grep ${T}
