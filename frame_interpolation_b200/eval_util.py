@@ -25,7 +25,8 @@ _UINT8_MAX_F = 255.0
 def read_image(filename: str) -> np.ndarray:
     """8-bit sRGB image file -> float32 (H, W, 3) RGB in [0, 1]."""
     import cv2
-    data = cv2.imread(filename, cv2.IMREAD_COLOR)      # BGR, uint8, alpha dropped, gray replicated
+    # BGR, uint8, alpha dropped, gray replicated; EXIF orientation ignored like tf.io.decode_image does
+    data = cv2.imread(filename, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
     if data is None:
         raise FileNotFoundError(f"cannot read image {filename}")
     rgb = np.ascontiguousarray(data[..., ::-1])
@@ -63,7 +64,9 @@ def _pair_sequence(frame_a: np.ndarray, frame_b: np.ndarray, times: int, interpo
         seq = fast(frame_a, frame_b, times)
         if on_frame:
             on_frame((1 << times) - 1)
-        return [seq[i] for i in range(seq.shape[0] - 1)]
+        # copies, not views: `seq` is one page-locked (2^times + 1)-frame buffer of the engine's pool, and a caller
+        # holding a single frame must not keep hundreds of MB of pinned memory alive
+        return [np.array(seq[i]) for i in range(seq.shape[0] - 1)]
     # generic path: explicit stack instead of recursion, same calls and same order of results
     dt = np.full((1,), 0.5, np.float32)
     frames = [frame_a, frame_b]

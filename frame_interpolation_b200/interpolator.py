@@ -94,9 +94,14 @@ class Interpolator:
     def __init__(self, model_path: str, align: Optional[int] = None,
                  block_shape: Optional[List[int]] = None, device: int = 0) -> None:
         self._lib = _lib.load()
-        if model_path is None or str(model_path).startswith("synthetic"):
+        if model_path is None:
+            # the reference fails without a SavedModel; silently substituting random weights would produce
+            # plausible-looking garbage frames
+            raise ValueError("model_path is required: a FILMW1 weight file (tf_bundle.convert_saved_model), or the "
+                             "explicit string 'synthetic[:seed]' for seeded random weights (tests / benchmarks only)")
+        if str(model_path).startswith("synthetic"):
             seed = 1234
-            if model_path and ":" in str(model_path):
+            if ":" in str(model_path):
                 seed = int(str(model_path).split(":", 1)[1])
             model_path = _weights.ensure_synthetic_file(seed=seed)
         self._handle = C.c_void_p()

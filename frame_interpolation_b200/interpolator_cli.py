@@ -28,7 +28,9 @@ _INPUT_EXT = ["png", "jpg", "jpeg"]
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     p.add_argument("--pattern", required=True, help="The pattern to determine the directories with the input frames.")
-    p.add_argument("--model_path", default="synthetic", help="FILMW1 weight file (or 'synthetic').")
+    p.add_argument("--model_path", required=True,
+                   help="FILMW1 weight file (tf_bundle.convert_saved_model output), or 'synthetic[:seed]' to opt in to "
+                        "seeded random weights (plumbing tests only: the frames are meaningless).")
     p.add_argument("--times_to_interpolate", type=int, default=5,
                    help="Number of recursive midpoint interpolations; output has 2^times+1 frames per input pair.")
     p.add_argument("--fps", type=int, default=30)
@@ -40,41 +42,59 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
-def output_frames(frames: List[np.ndarray], frames_dir: str) -> None:
-    """Writes frame_%03d.png; stale frame_*.png files of a previous run are removed first."""
-    if os.path.isdir(frames_dir):
-        for old in glob.glob(os.path.join(frames_dir, "frame_*.png")):
-            os.remove(old)
-    else:
-        os.makedirs(frames_dir)
-    for idx, frame in enumerate(frames):
-        eval_util.write_image(os.path.join(frames_dir, f"frame_{idx:03d}.png"), frame)
+class _VideoWriter:
+    """Raw RGB frames piped to ffmpeg as they are produced; a failed encode raises with ffmpeg's own message."""
 
+    def __init__(self, path: str, h: int, w: int, fps: int):
+        ffmpeg = eval_util.get_ffmpeg_path()
+        self.path = path
+        # yuv420p needs even dimensions: pad by one replicated row/column instead of failing silently
+        cmd = [ffmpeg, "-y", "-f", "rawvideo", "-pix_fmt", "rgb24", "-s", f"{w}x{h}", "-r", str(fps), "-i", "-",
+               "-vf", "pad=ceil(iw/2)*2:ceil(ih/2)*2", "-pix_fmt", "yuv420p", path]
+        self.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
 
-def write_video(path: str, frames: List[np.ndarray], fps: int) -> None:
-    ffmpeg = eval_util.get_ffmpeg_path()
-    h, w, _ = frames[0].shape
-    cmd = [ffmpeg, "-y", "-f", "rawvideo", "-pix_fmt", "rgb24", "-s", f"{w}x{h}", "-r", str(fps), "-i", "-",
-           "-pix_fmt", "yuv420p", path]
-    proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    for f in frames:
-        proc.stdin.write(eval_util.to_uint8(f).tobytes())
-    proc.stdin.close()
-    proc.wait()
+    def write(self, frame: np.ndarray) -> None:
+        try:
+            self.proc.stdin.write(eval_util.to_uint8(frame).tobytes())
+        except BrokenPipeError:
+            self.close()
+
+    def close(self) -> None:
+        if self.proc.stdin and not self.proc.stdin.closed:
+            self.proc.stdin.close()
+        err = self.proc.stderr.read().decode(errors="replace")
+        rc = self.proc.wait()
+        if rc != 0:
+            raise RuntimeError(f"ffmpeg failed (exit {rc}) writing {self.path}: {err[-2000:]}")
 
 
 def process_directory(directory: str, interpolator: Interpolator, times: int, fps: int, video: bool) -> int:
+    """Frames are written (and piped to ffmpeg) as the generator yields them: nothing but the current input pair's
+    sequence is ever held in memory (eval/interpolator_cli.py:164-177 materialises the whole list)."""
     names: List[str] = []
     for ext in _INPUT_EXT:
         names += eval_util.natural_sorted(glob.glob(os.path.join(directory, f"*.{ext}")))
     if len(names) < 2:
         print(f"[film_b200] {directory}: fewer than two input frames, skipped", file=sys.stderr)
         return 0
-    frames = list(eval_util.interpolate_recursively_from_files(names, times, interpolator))
-    output_frames(frames, os.path.join(directory, "interpolated_frames"))
-    if video:
-        write_video(os.path.join(directory, "interpolated.mp4"), frames, fps)
-    return len(frames)
+    frames_dir = os.path.join(directory, "interpolated_frames")
+    if os.path.isdir(frames_dir):
+        for old in glob.glob(os.path.join(frames_dir, "frame_*.png")):   # stale frames of a previous run
+            os.remove(old)
+    else:
+        os.makedirs(frames_dir)
+    writer = None
+    n = 0
+    for frame in eval_util.interpolate_recursively_from_files(names, times, interpolator):
+        eval_util.write_image(os.path.join(frames_dir, f"frame_{n:03d}.png"), frame)
+        if video:
+            if writer is None:
+                writer = _VideoWriter(os.path.join(directory, "interpolated.mp4"), frame.shape[0], frame.shape[1], fps)
+            writer.write(frame)
+        n += 1
+    if writer is not None:
+        writer.close()
+    return n
 
 
 def main(argv=None) -> int:

@@ -205,11 +205,11 @@ def film_weights_from_bundle(tensors: Mapping[str, np.ndarray]) -> Dict[str, np.
             continue
         named[k] = arr
     if len(out) < len(table):
-        try:
-            for k, v in W.from_named_arrays({**named, **out}).items():
-                out.setdefault(k, v)
-        except ValueError:
-            pass
+        # Mixed / variable-name keys: take table-named tensors directly, and resolve the fusion convs' Keras
+        # auto-names (`fusion/conv2d_<n>`, a GLOBAL counter that need not start at 0) by creation order --
+        # independently of each other, so one missing group cannot hide what the other one found.
+        for k, v in W.from_named_arrays(named, partial=True).items():
+            out.setdefault(k, v)
     missing = sorted(set(table) - set(out))
     if missing:
         raise ValueError(f"bundle does not contain the FILM variables: missing {missing[:4]} ... "

@@ -110,8 +110,11 @@ def synthetic_weights(seed: int = 1234) -> Dict[str, np.ndarray]:
     return out
 
 
-def from_named_arrays(arrays: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]:
+def from_named_arrays(arrays: Mapping[str, np.ndarray], partial: bool = False) -> Dict[str, np.ndarray]:
     """Map SavedModel variable names to the engine's table.
+
+    `partial=True` returns whatever could be mapped (no completeness / shape check): used by the
+    TensorBundle importer to merge with keys it resolved another way.
 
     Accepts the reference's variable names. Feature-extractor and flow-predictor
     variables carry explicit layer names; fusion convs are unnamed Keras layers
@@ -143,13 +146,24 @@ def from_named_arrays(arrays: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]
     names = [f"fusion/level_{i}/conv_{j}" for i in range(spec.FUSION_PYRAMID_LEVELS - 1)
              for j in range(3)] + ["fusion/output_conv"]
     if order and len(order) != len(names):
+        if partial:
+            return out
         raise ValueError(f"expected {len(names)} fusion convs, found {len(order)}")
     for idx, nm in zip(order, names):
         layer = fusion_layers[idx]
         if "kernel" not in layer or "bias" not in layer:
+            if partial:
+                continue
             raise ValueError(f"fusion conv #{idx} is missing its kernel or bias")
+        # creation order must also agree with the shapes (a reordered counter would be caught here)
+        if tuple(layer["kernel"].shape) != tuple(table[nm + "/kernel"]):
+            if partial:
+                continue
+            raise ValueError(f"fusion conv #{idx} ({nm}): kernel shape {layer['kernel'].shape} != {table[nm + '/kernel']}")
         out[nm + "/kernel"] = layer["kernel"]
         out[nm + "/bias"] = layer["bias"]
+    if partial:
+        return out
     missing = set(table) - set(out)
     if missing:
         raise ValueError(f"missing variables: {sorted(missing)[:5]} ...")

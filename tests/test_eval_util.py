@@ -56,7 +56,9 @@ def test_natural_sort():
 
 
 def test_cli_flags_match_the_reference():
-    a = interpolator_cli.build_parser().parse_args(["--pattern", "x/*"])
+    with pytest.raises(SystemExit):                      # like the reference, --model_path is required:
+        interpolator_cli.build_parser().parse_args(["--pattern", "x/*"])   # no silent random weights
+    a = interpolator_cli.build_parser().parse_args(["--pattern", "x/*", "--model_path", "synthetic"])
     assert (a.times_to_interpolate, a.fps, a.align, a.block_height, a.block_width, a.output_video) == (5, 30, 64, 1, 1, False)
     a = interpolator_cli.build_parser().parse_args(
         ["--pattern", "x", "--model_path", "m", "--times_to_interpolate", "2", "--block_height", "2",

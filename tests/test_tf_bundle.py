@@ -104,3 +104,96 @@ def test_saved_model_conversion_variable_name_keys(tmp_path):
     tf_bundle.write_bundle(prefix, named)
     with pytest.raises(ValueError, match="missing"):
         tf_bundle.film_weights_from_bundle(tf_bundle.read_bundle(prefix))
+
+
+def _fixture_keys():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "film_style_object_graph_keys.tsv")
+    rows = []
+    for line in open(path):
+        if line.startswith("#") or not line.strip():
+            continue
+        key, dtype, shape = line.rstrip("\n").split("\t")
+        shape = () if shape in ("()", "") else tuple(int(d) for d in shape.split(","))
+        rows.append((key, dtype, shape))
+    return rows
+
+
+def test_object_graph_key_list_fixture_maps_onto_the_whole_weight_table(tmp_path):
+    """The committed key list (object-graph style: `layer_with_weights-N/<attribute path>/.ATTRIBUTES/VARIABLE_VALUE`,
+    plus optimizer slots, counters and the object-graph proto) is written as a real TensorBundle with seeded values and
+    read back through the importer: every one of the 82 engine tensors must be found, with the right shape, from the
+    right key, and nothing else may leak in."""
+    rng = np.random.default_rng(5)
+    tensors, by_key = {}, {}
+    for key, dtype, shape in _fixture_keys():
+        if dtype == "string":
+            tensors[key] = np.zeros(8, np.uint8)          # stand-in for the serialized object graph
+        elif dtype == "int64":
+            tensors[key] = np.array(3, np.int64)
+        else:
+            tensors[key] = rng.standard_normal(shape).astype(np.float32) if shape else np.array(0.5, np.float32)
+    prefix = str(tmp_path / "saved_model" / "variables" / "variables")
+    tf_bundle.write_bundle(prefix, tensors, with_crc=True)
+    got = tf_bundle.film_weights_from_bundle(tf_bundle.read_bundle(prefix))
+    table = dict(spec.weight_table())
+    assert set(got) == set(table) and len(got) == 82
+    for name, shape in table.items():
+        assert got[name].shape == tuple(shape)
+    # spot checks of the attribute-path mapping, including the shared predictor (list index 3)
+    suf = "/.ATTRIBUTES/VARIABLE_VALUE"
+    np.testing.assert_array_equal(got["feat_net/sub_extractor/cfeat_conv_5/kernel"],
+                                  tensors["layer_with_weights-0/extract_sublevels/convs/5/kernel" + suf])
+    np.testing.assert_array_equal(got["predict_flow/flow_predictor_shared/conv_4/bias"],
+                                  tensors["layer_with_weights-1/_predictors/3/_convs/4/bias" + suf])
+    np.testing.assert_array_equal(got["fusion/level_2/conv_0/kernel"],
+                                  tensors["layer_with_weights-2/convs/2/0/kernel" + suf])
+    np.testing.assert_array_equal(got["fusion/output_conv/kernel"], tensors["layer_with_weights-2/output_conv/kernel" + suf])
+    # the optimizer slot of cfeat_conv_0 must not have replaced the variable itself
+    np.testing.assert_array_equal(got["feat_net/sub_extractor/cfeat_conv_0/kernel"],
+                                  tensors["layer_with_weights-0/extract_sublevels/convs/0/kernel" + suf])
+
+
+def _variable_name_keys(w, first_counter):
+    """Plain variable names; the fusion convs carry Keras auto-names `conv2d_<n>` from a GLOBAL counter."""
+    named, k = {}, first_counter
+    for name, _ in spec.weight_table():
+        if not name.endswith("/kernel"):
+            continue
+        base = name[:-len("/kernel")]
+        tf_name = base
+        if base.startswith("fusion/"):
+            tf_name = "fusion/conv2d" + ("" if k == 0 else f"_{k}")
+            k += 1
+        named[tf_name + "/kernel"] = w[base + "/kernel"]
+        named[tf_name + "/bias"] = w[base + "/bias"]
+    return named
+
+
+@pytest.mark.parametrize("first_counter", [0, 7, 98])
+def test_keras_auto_names_with_a_counter_that_does_not_start_at_zero(tmp_path, first_counter):
+    """`fusion/conv2d_7/kernel` ... `fusion/conv2d_19/kernel`: the counter is global to the Keras session (98 -> 110
+    also crosses a digit boundary, so a lexicographic sort would scramble the order)."""
+    w = weights.synthetic_weights(13)
+    prefix = str(tmp_path / "v" / "variables")
+    tf_bundle.write_bundle(prefix, _variable_name_keys(w, first_counter))
+    got = tf_bundle.film_weights_from_bundle(tf_bundle.read_bundle(prefix))
+    assert weights.digest(got) == weights.digest(w)
+
+
+def test_mixed_key_styles_are_merged_not_all_or_nothing(tmp_path):
+    """Fusion tensors under object-graph keys, feature/flow tensors under plain variable names: the importer must
+    take each group from where it finds it (the fallback used to drop the named group)."""
+    w = weights.synthetic_weights(14)
+    mixed = {k: v for k, v in _object_graph_keys(w).items() if "layer_with_weights-2" in k}
+    for name, _ in spec.weight_table():
+        if not name.startswith("fusion/"):
+            mixed["film_net/" + name + ":0"] = w[name]
+    prefix = str(tmp_path / "m" / "variables")
+    tf_bundle.write_bundle(prefix, mixed)
+    got = tf_bundle.film_weights_from_bundle(tf_bundle.read_bundle(prefix))
+    assert weights.digest(got) == weights.digest(w)
+    # a reordered Keras counter is caught by the shape check instead of silently permuting layers
+    named = _variable_name_keys(w, 0)
+    named["fusion/conv2d_1/kernel"], named["fusion/conv2d_2/kernel"] = named["fusion/conv2d_2/kernel"], named["fusion/conv2d_1/kernel"]
+    with pytest.raises(ValueError):
+        weights.from_named_arrays(named)
