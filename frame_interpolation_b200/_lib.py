@@ -17,6 +17,7 @@ EXPORTS = [
     "film_synchronize", "film_profile", "film_set_option",
     "film_debug_read", "film_op_table", "film_last_error", "film_version",
     "film_get_option", "film_stage_count", "film_stage_name",
+    "film_interpolate_u8", "film_interpolate_recursive_u8",
 ]
 
 
@@ -58,6 +59,11 @@ def load() -> C.CDLL:
     lib.film_interpolate_device.restype = C.c_int
     lib.film_interpolate_recursive.argtypes = [C.c_void_p, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]
     lib.film_interpolate_recursive.restype = C.c_int
+    up = C.POINTER(C.c_uint8)
+    lib.film_interpolate_u8.argtypes = [C.c_void_p, up, up, C.c_int, C.c_int, C.c_int, C.c_int, up]
+    lib.film_interpolate_u8.restype = C.c_int
+    lib.film_interpolate_recursive_u8.argtypes = [C.c_void_p, up, up, C.c_int, C.c_int, C.c_int, C.c_int, up]
+    lib.film_interpolate_recursive_u8.restype = C.c_int
     lib.film_host_alloc.argtypes = [C.c_size_t]
     lib.film_host_alloc.restype = C.c_void_p
     lib.film_host_free.argtypes = [C.c_void_p]

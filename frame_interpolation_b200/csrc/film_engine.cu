@@ -1125,6 +1125,8 @@ struct film_handle {
   int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
                          // persistent kernels (default), 3 also the 32-channel-chunk layers (experimental)
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
+  uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
+  size_t u8_bytes = 0;
   int num_sms = 148;
   std::vector<cudaEvent_t> op_events;
   film_profile_t prof;
@@ -1329,6 +1331,7 @@ void film_destroy(film_handle* h) {
     for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_free[i], h->ev_out[i]})
       if (e) cudaEventDestroy(e);
   }
+  if (h->u8_stage) cudaFree(h->u8_stage);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (int i = 1; i < Plan::kNumLanes; ++i)
@@ -1620,8 +1623,13 @@ int film_interpolate_tiled(film_handle* h, const float* x0, const float* x1, con
   FILM_CATCH_ALL(h)
 }
 
-int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W, int align,
-                               int times_to_interpolate, float* out) {
+extern "C++" {
+// Shared body of film_interpolate_recursive / film_interpolate_recursive_u8.  `u8`: the two input frames and the
+// 2^times + 1 output frames are 8-bit (eval/util.py:38-41 dequantisation on the way in, :51-52 quantisation on the
+// way out, both on the device); the recursion itself always runs on the unquantised float32 mid-frames, like
+// the reference (eval/util.py:85-91 passes the float mid-frame on, write_image quantises only what is saved).
+static int recursive_impl(film_handle* h, const void* frame0, const void* frame1, int H, int W, int align,
+                          int times_to_interpolate, void* out, bool u8) {
   if (!h) return FILM_ERR_ARG;
   try {
     check_frame_args(frame0, frame1, out, 1, H, W);
@@ -1630,17 +1638,32 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
     (void)cudaGetLastError();
     Plan* P = get_plan(h, H, W, align);
     const int n = (1 << times_to_interpolate) + 1;
-    const size_t frame = (size_t)H * W * 3 * sizeof(float);
+    const int64_t elems = (int64_t)H * W * 3;
+    const size_t frame = (size_t)elems * sizeof(float);
+    const size_t io_frame = u8 ? (size_t)elems : frame;   // bytes of one frame at the host boundary
     ensure_staging(h, 16);  // creates the copy stream
     std::vector<std::pair<int, cudaEvent_t>> frame_events;
     float* seq = nullptr;
+    uint8_t* q = nullptr;   // u8 mode: [2 input frames][n output frames]
     FILM_CUDA(cudaMalloc(&seq, frame * n));
+    if (u8 && cudaMalloc(&q, io_frame * (n + 2)) != cudaSuccess) {
+      cudaFree(seq);
+      throw Error{FILM_ERR_CUDA, "out of device memory for the 8-bit frame staging"};
+    }
     cudaError_t e = cudaSuccess;
     auto slot = [&](int i) { return (float*)((char*)seq + frame * i); };
+    auto qslot = [&](int i) { return q + io_frame * (size_t)(i + 2); };
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     chk(cudaEventRecord(h->ev[0], h->stream));
-    chk(cudaMemcpyAsync(slot(0), frame0, frame, cudaMemcpyHostToDevice, h->stream));
-    chk(cudaMemcpyAsync(slot(n - 1), frame1, frame, cudaMemcpyHostToDevice, h->stream));
+    if (u8) {
+      chk(cudaMemcpyAsync(q, frame0, io_frame, cudaMemcpyHostToDevice, h->stream));
+      chk(cudaMemcpyAsync(q + io_frame, frame1, io_frame, cudaMemcpyHostToDevice, h->stream));
+      chk(launch_u8_to_f32(q, slot(0), elems, h->stream));
+      chk(launch_u8_to_f32(q + io_frame, slot(n - 1), elems, h->stream));
+    } else {
+      chk(cudaMemcpyAsync(slot(0), frame0, frame, cudaMemcpyHostToDevice, h->stream));
+      chk(cudaMemcpyAsync(slot(n - 1), frame1, frame, cudaMemcpyHostToDevice, h->stream));
+    }
     chk(cudaEventRecord(h->ev[1], h->stream));
     // level-synchronous traversal of the binary tree of eval/util.py:62-91; every mid-frame stays in HBM
     for (int step = (n - 1) / 2; step >= 1 && e == cudaSuccess; step /= 2) {
@@ -1650,14 +1673,16 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
         if (e == cudaSuccess) {
           try {
             run_plan(h, P, h->stream);
-          } catch (const Error& err) {
+          } catch (...) {
             cudaStreamSynchronize(h->stream);
             for (auto& fe : frame_events) cudaEventDestroy(fe.second);
             cudaFree(seq);
+            if (q) cudaFree(q);
             throw;
           }
         }
         chk(cudaMemcpyAsync(slot(i), P->xout, frame, cudaMemcpyDeviceToDevice, h->stream));
+        if (u8) chk(launch_f32_to_u8(slot(i), qslot(i), elems, h->stream));
         if (e == cudaSuccess) {
           cudaEvent_t ev;
           chk(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1669,11 +1694,12 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
     chk(cudaEventRecord(h->ev[2], h->stream));
     // everything is enqueued; download each mid-frame as soon as it exists (copy stream), while the
     // deeper recursion levels are still computing
-    memcpy(out, frame0, frame);
-    memcpy((char*)out + frame * (n - 1), frame1, frame);
+    memcpy(out, frame0, io_frame);
+    memcpy((char*)out + io_frame * (n - 1), frame1, io_frame);
     for (auto& fe : frame_events) {
       chk(cudaStreamWaitEvent(h->copy_stream, fe.second, 0));
-      chk(cudaMemcpyAsync((char*)out + frame * fe.first, slot(fe.first), frame, cudaMemcpyDeviceToHost, h->copy_stream));
+      chk(cudaMemcpyAsync((char*)out + io_frame * fe.first, u8 ? (const void*)qslot(fe.first) : (const void*)slot(fe.first),
+                          io_frame, cudaMemcpyDeviceToHost, h->copy_stream));
     }
     chk(cudaStreamSynchronize(h->copy_stream));
     chk(cudaEventRecord(h->ev[3], h->stream));
@@ -1686,9 +1712,66 @@ int film_interpolate_recursive(film_handle* h, const float* frame0, const float*
       cudaEventElapsedTime(&t_d2h, h->ev[2], h->ev[3]);
     }
     cudaFree(seq);
+    if (q) cudaFree(q);
     FILM_CUDA(e);
     fill_profile(h, P, t_net, t_h2d, t_d2h);
     h->prof.kernel_launches = (int64_t)P->ops.size() * (n - 2);
+    return FILM_OK;
+  }
+  FILM_CATCH_ALL(h)
+}
+}  // extern "C++"
+
+int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W, int align,
+                               int times_to_interpolate, float* out) {
+  return recursive_impl(h, frame0, frame1, H, W, align, times_to_interpolate, out, false);
+}
+
+int film_interpolate_recursive_u8(film_handle* h, const uint8_t* frame0, const uint8_t* frame1, int H, int W, int align,
+                                  int times_to_interpolate, uint8_t* out) {
+  return recursive_impl(h, frame0, frame1, H, W, align, times_to_interpolate, out, true);
+}
+
+int film_interpolate_u8(film_handle* h, const uint8_t* x0, const uint8_t* x1, int B, int H, int W, int align,
+                        uint8_t* out) {
+  if (!h) return FILM_ERR_ARG;
+  try {
+    check_frame_args(x0, x1, out, B, H, W);
+    FILM_CUDA(cudaSetDevice(h->device));
+    (void)cudaGetLastError();
+    Plan* P = get_plan(h, H, W, align);
+    const int64_t elems = (int64_t)H * W * 3;
+    if (h->u8_bytes < (size_t)elems * 3) {   // [x0][x1][out] 8-bit staging on the device
+      if (h->u8_stage) cudaFree(h->u8_stage);
+      h->u8_stage = nullptr;
+      h->u8_bytes = 0;
+      FILM_CUDA(cudaMalloc(&h->u8_stage, (size_t)elems * 3));
+      h->u8_bytes = (size_t)elems * 3;
+    }
+    uint8_t* q = h->u8_stage;
+    float ms_net = 0, ms_h2d = 0, ms_d2h = 0;
+    for (int b = 0; b < B; ++b) {
+      FILM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+      FILM_CUDA(cudaMemcpyAsync(q, x0 + (int64_t)b * elems, elems, cudaMemcpyHostToDevice, h->stream));
+      FILM_CUDA(cudaMemcpyAsync(q + elems, x1 + (int64_t)b * elems, elems, cudaMemcpyHostToDevice, h->stream));
+      FILM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+      FILM_CUDA(launch_u8_to_f32(q, P->xin, elems, h->stream));            // eval/util.py:38-41
+      FILM_CUDA(launch_u8_to_f32(q + elems, P->xin + elems, elems, h->stream));
+      run_plan(h, P, h->stream);
+      FILM_CUDA(launch_f32_to_u8(P->xout, q + 2 * elems, elems, h->stream));  // eval/util.py:51-52
+      FILM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+      FILM_CUDA(cudaMemcpyAsync(out + (int64_t)b * elems, q + 2 * elems, elems, cudaMemcpyDeviceToHost, h->stream));
+      FILM_CUDA(cudaEventRecord(h->ev[3], h->stream));
+      FILM_CUDA(cudaStreamSynchronize(h->stream));
+      float t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+      ms_h2d += t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[1], h->ev[2]));
+      ms_net += t;
+      FILM_CUDA(cudaEventElapsedTime(&t, h->ev[2], h->ev[3]));
+      ms_d2h += t;
+    }
+    fill_profile(h, P, ms_net, ms_h2d, ms_d2h);
     return FILM_OK;
   }
   FILM_CATCH_ALL(h)

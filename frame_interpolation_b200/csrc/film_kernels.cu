@@ -63,6 +63,58 @@ cudaError_t launch_pad_image(const float* src, int64_t src_pitch, int h, int w, 
 }
 
 // ------------------------------------------------------------------------------------------
+// 8-bit front / back end.  eval/util.py:38-41: image = uint8 / 255 (float32 division);
+// eval/util.py:51-52: uint8 = trunc(clip(image * 255, 0, 255) + 0.5), every step rounded to float32 like numpy.
+// ------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(256) k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (kVec && i + 3 < n) {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(src + i);
+    float4 f;
+    f.x = __fdiv_rn((float)u.x, 255.f);
+    f.y = __fdiv_rn((float)u.y, 255.f);
+    f.z = __fdiv_rn((float)u.z, 255.f);
+    f.w = __fdiv_rn((float)u.w, 255.f);
+    *reinterpret_cast<float4*>(dst + i) = f;
+  } else {
+    for (int64_t j = i; j < n && j < i + 4; ++j) dst[j] = __fdiv_rn((float)src[j], 255.f);
+  }
+}
+__device__ __forceinline__ uint8_t quantize_u8(float x) {
+  const float s = fminf(fmaxf(__fmul_rn(x, 255.f), 0.f), 255.f);
+  return (uint8_t)__fadd_rn(s, 0.5f);  // truncation, like numpy's astype(uint8)
+}
+template <bool kVec>
+__global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (kVec && i + 3 < n) {
+    const float4 f = *reinterpret_cast<const float4*>(src + i);
+    uchar4 u;
+    u.x = quantize_u8(f.x);
+    u.y = quantize_u8(f.y);
+    u.z = quantize_u8(f.z);
+    u.w = quantize_u8(f.w);
+    *reinterpret_cast<uchar4*>(dst + i) = u;
+  } else {
+    for (int64_t j = i; j < n && j < i + 4; ++j) dst[j] = quantize_u8(src[j]);
+  }
+}
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, int64_t n, cudaStream_t st) {
+  // vector accesses need a 4-byte aligned source and a 16-byte aligned destination (frame slots of odd sizes are not)
+  const bool vec = ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 15) == 0;
+  if (vec) k_u8_to_f32<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(src, dst, n);
+  else k_u8_to_f32<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_to_u8(const float* src, uint8_t* dst, int64_t n, cudaStream_t st) {
+  const bool vec = ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 3) == 0;
+  if (vec) k_f32_to_u8<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(src, dst, n);
+  else k_f32_to_u8<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // feature_extractor.py:119  cfeat_conv_0: 3 -> 64, 3x3 SAME + bias + LeakyReLU, fp32 math.
 // 8 threads per pixel (8 output channels each); 32 pixels per 256-thread block.
 // ------------------------------------------------------------------------------------------

@@ -60,6 +60,10 @@ cudaError_t launch_rgb_head(const sp_t* x_hi, const sp_t* x_lo, int Cx, int H, i
 cudaError_t launch_pad_image(const float* src, int64_t src_pitch, int h, int w, float* dst, int H,
                              int W, int off_y, int off_x, cudaStream_t st);
 
+// 8-bit front / back end: eval/util.py:38-41 (uint8 / 255 -> float32) and :51-52 (clip(x * 255, 0, 255) + 0.5 -> uint8)
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, int64_t n, cudaStream_t st);
+cudaError_t launch_f32_to_u8(const float* src, uint8_t* dst, int64_t n, cudaStream_t st);
+
 // debug: split tensor slice -> fp32 NHWC
 cudaError_t launch_unsplit(const sp_t* hi, const sp_t* lo, int C, int c_off, int Cn, int64_t npix,
                            float* out, cudaStream_t st);

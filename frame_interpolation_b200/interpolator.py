@@ -217,6 +217,41 @@ class Interpolator:
         self._check(st)
         return out
 
+    def interpolate_u8(self, x0: np.ndarray, x1: np.ndarray) -> np.ndarray:
+        """8-bit in / 8-bit out: (B, H, W, 3) uint8 frames; the /255 of `read_image` (eval/util.py:38-41) and the
+        quantisation of `write_image` (eval/util.py:51-52) run on the device, so PCIe carries a quarter of the bytes.
+        Bit-identical to `to_uint8(self(x0 / 255, x1 / 255, dt))`. Untiled path."""
+        if self._align is not None:
+            assert self._align > 0, 'align must be a positive number.'
+        assert np.ndim(x0) == 4 and np.ndim(x1) == 4, "expected (batch, height, width, channels)"
+        x0 = np.ascontiguousarray(x0, dtype=np.uint8)
+        x1 = np.ascontiguousarray(x1, dtype=np.uint8)
+        assert x0.shape == x1.shape and x0.shape[-1] == 3
+        b, h, w, _ = x0.shape
+        out = np.empty(x0.shape, np.uint8)
+        up = C.POINTER(C.c_uint8)
+        st = self._lib.film_interpolate_u8(self._handle, x0.ctypes.data_as(up), x1.ctypes.data_as(up), b, h, w,
+                                           int(self._align or 0), out.ctypes.data_as(up))
+        self._check(st)
+        return out
+
+    def interpolate_recursively_u8(self, frame0: np.ndarray, frame1: np.ndarray, times_to_interpolate: int) -> np.ndarray:
+        """`interpolate_recursively` with uint8 frames at the boundary: (2**times + 1, H, W, 3) uint8, end points included.
+        The recursion runs on the unquantised float32 mid-frames (eval/util.py:85-91); only the returned frames are quantised."""
+        if self._align is not None:
+            assert self._align > 0, 'align must be a positive number.'
+        f0 = np.ascontiguousarray(frame0, dtype=np.uint8)
+        f1 = np.ascontiguousarray(frame1, dtype=np.uint8)
+        assert f0.ndim == 3 and f0.shape == f1.shape and f0.shape[-1] == 3, "expected two (H, W, 3) uint8 frames"
+        h, w, _ = f0.shape
+        n = (1 << int(times_to_interpolate)) + 1
+        out = np.empty((n, h, w, 3), np.uint8)
+        up = C.POINTER(C.c_uint8)
+        st = self._lib.film_interpolate_recursive_u8(self._handle, f0.ctypes.data_as(up), f1.ctypes.data_as(up), h, w,
+                                                     int(self._align or 0), int(times_to_interpolate), out.ctypes.data_as(up))
+        self._check(st)
+        return out
+
     def synchronize(self) -> None:
         self._check(self._lib.film_synchronize(self._handle))
 

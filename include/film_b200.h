@@ -112,6 +112,17 @@ FILM_API int film_interpolate_device(film_handle* h, const float* d_x0, const fl
 FILM_API int film_interpolate_recursive(film_handle* h, const float* frame0, const float* frame1, int H, int W,
                                         int align, int times_to_interpolate, float* out);
 
+/* 8-bit front / back end: the frames cross PCIe as uint8 (4x fewer bytes) and the reference's
+ * conversions run on the device, bit-identical to the host versions:
+ *   in : float32 = uint8 / 255                         (eval/util.py:38-41, read_image)
+ *   out: uint8   = trunc(clip(x * 255, 0, 255) + 0.5)  (eval/util.py:51-52, write_image)
+ * film_interpolate_u8 == to_uint8(film_interpolate(x0 / 255, x1 / 255)).  film_interpolate_recursive_u8 keeps the
+ * recursion on the unquantised float32 mid-frames (like eval/util.py:85-91) and quantises only what it returns. */
+FILM_API int film_interpolate_u8(film_handle* h, const uint8_t* x0, const uint8_t* x1, int B, int H, int W, int align,
+                                 uint8_t* out);
+FILM_API int film_interpolate_recursive_u8(film_handle* h, const uint8_t* frame0, const uint8_t* frame1, int H, int W,
+                                           int align, int times_to_interpolate, uint8_t* out);
+
 /* Page-locked host memory for frames (cudaHostAlloc): uploads / downloads of pinned buffers run at
  * PCIe speed instead of through the driver's pageable staging path. The Python wrapper returns its
  * results in pooled buffers allocated here. NULL on failure. */

@@ -449,3 +449,23 @@ def test_4k_tiled_2x2_at_real_tile_size(synthetic_weights):
     assert err < PLAN, err
     eng.close()
     single.close()
+
+
+@pytest.mark.parametrize("h,w", [(96, 160), (65, 129)])
+def test_u8_front_and_back_end_bit_identical_to_the_host_conversions(engine, h, w):
+    """film_interpolate_u8 / _recursive_u8: uint8 frames cross PCIe, `/255` (eval/util.py:38-41) and
+    `clip(x*255,0,255)+0.5 -> uint8` (eval/util.py:51-52) run on the device. Must equal the float path wrapped in the
+    host-side conversions bit for bit (65x129: frame slots that are not 16-byte aligned take the scalar kernels)."""
+    from frame_interpolation_b200 import eval_util
+    x0, x1 = synthetic.frame_pair(h, w, seed=17, n_waves=8)
+    u0, u1 = eval_util.to_uint8(x0), eval_util.to_uint8(x1)
+    f0 = u0.astype(np.float32) / np.float32(255.0)
+    f1 = u1.astype(np.float32) / np.float32(255.0)
+    got = engine.interpolate_u8(u0, u1)
+    assert got.dtype == np.uint8 and got.shape == u0.shape
+    np.testing.assert_array_equal(got, eval_util.to_uint8(engine(f0, f1, DT)))
+    seq = engine.interpolate_recursively_u8(u0[0], u1[0], 3)
+    assert seq.shape == (9, h, w, 3) and seq.dtype == np.uint8
+    np.testing.assert_array_equal(seq, eval_util.to_uint8(engine.interpolate_recursively(f0[0], f1[0], 3)))
+    np.testing.assert_array_equal(seq[0], u0[0])
+    np.testing.assert_array_equal(seq[-1], u1[0])
