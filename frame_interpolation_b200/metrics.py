@@ -8,6 +8,16 @@ from __future__ import annotations
 import numpy as np
 
 
+def l1(a: np.ndarray, b: np.ndarray) -> float:
+    """losses.py:72-74 (l1_loss): mean absolute difference."""
+    return float(np.mean(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))
+
+
+def l2(a: np.ndarray, b: np.ndarray) -> float:
+    """losses.py:98-100 (l2_loss): mean squared difference."""
+    return float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+
+
 def psnr(a: np.ndarray, b: np.ndarray, max_val: float = 1.0) -> float:
     """10 * log10(max_val^2 / mse), mse over the last three axes (per image), averaged over the batch."""
     a = np.asarray(a, np.float64)
