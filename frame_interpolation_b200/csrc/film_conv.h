@@ -61,7 +61,13 @@ struct alignas(64) ConvProblem {
   // epilogue mode 1 ("flow head", pyramid_flow_estimator.py:77-83,161): this conv is the 1x1
   // nf -> nf/2 LeakyReLU layer; the epilogue applies the final linear 1x1 (nf/2 -> 2) on the
   // fp32 accumulators and adds the upsampled flow:  res = W4^T h + b4 ;  v = res + v_up.
+  // epilogue mode 2 ("RGB head", fusion.py:100-101,139 + the crop of eval/interpolator.py:175; persistent single-CTA
+  // kernel only): this conv is the decoder's last 3x3 (64 -> 64, LeakyReLU); the epilogue applies the linear 1x1
+  // 64 -> 3 output conv on the fp32 activations and writes the cropped fp32 image -- the 64-channel tensor is never
+  // stored.  head_w4 = [64][3], head_b4 = [3], head_v = image [crop_h][crop_w][3] with row pitch crop_pitch floats.
   int epi_mode;
+  int crop_y, crop_x, crop_h, crop_w;
+  int64_t crop_pitch;
   const float* head_w4;   // [cout][2]
   const float* head_b4;   // [2]
   const float* head_vup;  // [B][H][W][2] or null (coarsest level)

@@ -330,6 +330,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     const int pool_C = prob->pool_C;
     const bool do_pool = pool_hi != nullptr;
     const bool lo_skip = prob->out_lo_skip != 0;
+    // RGB-head mode: channel partial sums of the 1x1 64 -> 3 conv; the two warps of a lane quarter own 32 channels each
+    // and combine through shared memory (named barrier per quarter)
+    const bool rgb = prob->epi_mode == 2;
+    const float* const head_w = prob->head_w4;
+    float* const rgb_out = prob->head_v;
+    const int crop_y = prob->crop_y, crop_x = prob->crop_x, crop_h = prob->crop_h, crop_w = prob->crop_w;
+    const int64_t crop_pitch = prob->crop_pitch;
+    float* const part = bias_smem + 64;   // [128 rows][3] (bias_smem holds 64 biases in this mode, 512 floats in all)
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
@@ -343,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       mbar_wait(tail + 8u * (4 * kMaxRing + acc), (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
       for (int cc = half; cc < BN / 16; cc += 2) {
         if (n0 + cc * 16 >= cout) break;
@@ -364,7 +373,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             float x = __uint_as_float(v[j]) + bias_smem[n0 + cc * 16 + j];
             f[j] = act ? leaky(x) : x;
           }
-          if (valid) {
+          if (rgb) {
+            const float* hw = head_w + (n0 + cc * 16) * 3;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              r0 = fmaf(f[j], __ldg(hw + 3 * j), r0);
+              r1 = fmaf(f[j], __ldg(hw + 3 * j + 1), r1);
+              r2 = fmaf(f[j], __ldg(hw + 3 * j + 2), r2);
+            }
+          } else if (valid) {
             if (lo_skip) pack_store16_hi(f, oh + cc * 16);
             else pack_store16(f, oh + cc * 16, ol + cc * 16);   // two 32-byte stores
           }
@@ -387,6 +404,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tail + 8u * (4 * kMaxRing + 2 + acc));
+      if (rgb) {
+        if (half == 1) {
+          part[r * 3] = r0;
+          part[r * 3 + 1] = r1;
+          part[r * 3 + 2] = r2;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        if (half == 0) {
+          const int oy = py - crop_y, ox = px - crop_x;
+          if (valid && oy >= 0 && oy < crop_h && ox >= 0 && ox < crop_w) {
+            float* o = rgb_out + (int64_t)oy * crop_pitch + (int64_t)ox * 3;
+            o[0] = r0 + part[r * 3] + __ldg(prob->head_b4);
+            o[1] = r1 + part[r * 3 + 1] + __ldg(prob->head_b4 + 1);
+            o[2] = r2 + part[r * 3 + 2] + __ldg(prob->head_b4 + 2);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // part[] is rewritten by the next tile
+      }
     }
   }
   tc_fence_before();

@@ -464,6 +464,8 @@ struct Plan {
   int conv3x3_v2 = 1, num_sms = 148, conv3x3_2cta = 0;
   int conv3x3_halo = 0;  // 1: pair kernel, 2: + single-CTA persistent kernel, 3: + 32-channel-chunk layers
   uint32_t onepass_mask = 0;  // precision plan: stages on the single-pass product
+  int fe_conv0_tc = 0;        // 1: cfeat_conv_0 on the tensor cores (32-channel-padded image), 0: fp32 FMA kernel
+  int fuse_rgb_head = 1;      // RGB head + crop in the epilogue of the decoder's last conv
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -574,7 +576,7 @@ static void pick_tile(int H, int W, int& th, int& tw) {
 static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, const PackedConv& pc,
                        const std::vector<SrcRef>& sources, int act, const SplitBuf* out, int out_c_off,
                        int stage, int consumer, int sy = 1, int sx = 1, int oy = 0, int ox = 0,
-                       const SplitBuf* pool_out = nullptr, bool no_op = false) {
+                       const SplitBuf* pool_out = nullptr, bool no_op = false, int epi_mode = 0) {
   // `stage`: precision-plan stage of this conv.  `consumer`: stage of the ONLY reader of the destination when that
   // reader is a conv (ST_NONE otherwise): a single-pass reader never touches the lo plane, so it is not written.
   ConvProblem cp;
@@ -590,11 +592,12 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   // 3x3 SAME convs with a unit-stride destination run on the persistent tap-reuse kernel
   const int kc = pc.kchunk;
   cp.kchunk = kc;
-  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && out && sy == 1 && sx == 1 &&
+  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && (out || epi_mode == 2) && sy == 1 && sx == 1 &&
                   (kc == kChunk || pc.cout <= 64);
+  cp.epi_mode = epi_mode;
   int box_h, box_w;
   // CTA-pair kernel: large levels only (it needs 16x8 tiles and enough tile pairs to fill the SM pairs)
-  const bool want_pair = v2 && P.conv3x3_2cta &&
+  const bool want_pair = v2 && P.conv3x3_2cta && epi_mode != 2 &&   // (the RGB-head epilogue lives in the single-CTA kernel)
                          (P.conv3x3_2cta >= 2 ||  // >= 2: every eligible layer (testing)
                           (long)cp.B * ((cp.H + 15) / 16) * ((cp.W + 7) / 8) >= 4L * P.num_sms);
   if (v2) {
@@ -722,9 +725,11 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
 
 static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align, int conv_impl, bool keep_debug,
                                         int conv3x3_v2, int num_sms, int conv3x3_2cta, int conv3x3_halo,
-                                        uint32_t onepass_mask, bool use_lanes) {
+                                        uint32_t onepass_mask, bool use_lanes, int fe_conv0_tc) {
   std::unique_ptr<Plan> pl(new Plan);
   Plan& P = *pl;
+  P.fe_conv0_tc = fe_conv0_tc & 1;
+  P.fuse_rgb_head = (fe_conv0_tc & 2) ? 0 : 1;
   P.onepass_mask = onepass_mask;
   P.reuse = !keep_debug && !use_lanes;
   P.h = h;
@@ -793,7 +798,17 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     for (int j = 0; j < depth; ++j) {
       const int r = i + j, c = kFilters << j;
       SplitBuf* t1 = P.split(2, Hs[r], Ws[r], c);
-      if (j == 0 && P.conv_impl == 0 && P.conv3x3_v2) {
+      if (j == 0 && P.conv_impl == 0 && !P.fe_conv0_tc) {
+        // cfeat_conv_0 (K = 27) on the FMA pipes, straight from the fp32 image level (exact fp32 arithmetic)
+        const float* im = img[i];
+        const int hh = Hs[r], ww = Ws[r];
+        const float *w0 = M.conv0_w, *b0 = M.conv0_b;
+        sp_t *oh = t1->hi, *ol = t1->lo;
+        const bool lo_skip = (P.onepass_mask >> fe_stage(i, 1)) & 1u;   // only reader: cfeat_conv_1 of this sub-tree
+        P.add_op(2, "fe_conv0@L" + std::to_string(r),
+                 [=](cudaStream_t st) { return launch_fe_conv0(im, 2, hh, ww, w0, b0, oh, ol, lo_skip, st); },
+                 2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 * 4 + 64 * (lo_skip ? 2.0 : 4.0)));
+      } else if (j == 0 && P.conv_impl == 0 && P.conv3x3_v2) {
         // cfeat_conv_0 on the persistent 3x3 tensor-core kernel: the image is widened to a 32-channel
         // split tensor (3 real channels), K = 9 taps x one 32-channel block
         const float* im = img[i];
@@ -1026,28 +1041,47 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
                    4.0 * M.fus_up[i][0].cin_ref * nf, M.fus_up[i][py * 2 + px], up_src, 0, up, 0, ST_FUS + 3 * i,
                    ST_FUS + 3 * i + 1, 2, 2, py, px);
     }
+    const bool fuse_rgb = (i == 0) && P.conv_impl == 0 && P.conv3x3_v2 && P.fuse_rgb_head && !keep_debug;
     SplitBuf* f1 = P.split(1, hh, ww, cpad);
-    SplitBuf* f2 = P.split(1, hh, ww, cpad);
+    SplitBuf* f2 = fuse_rgb ? nullptr : P.split(1, hh, ww, cpad);
     add_conv(P, "fusion_conv1@L" + std::to_string(i), 9.0 * M.fus_c1[i].cin_ref * nf, M.fus_c1[i],
              {{batch_view(wf[i], 0), 0}, {batch_view(wf[i], 1), 0}, {side[i], 0}, {up, 0}}, 1, f1, 0, ST_FUS + 3 * i + 1,
              ST_FUS + 3 * i + 2);
-    add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0, ST_FUS + 3 * i + 2,
-             i > 0 ? ST_FUS + 3 * (i - 1) : ST_NONE);
+    if (fuse_rgb) {
+      // last decoder conv with the RGB head (fusion.py:100-101,139) and the crop (eval/interpolator.py:175) in its
+      // epilogue: the 64-channel activation is never written
+      const size_t ci = add_conv(P, "fusion_conv2+rgb@L0", 9.0 * nf * nf + 64.0 * 3, M.fus_c2[i], {{f1, 0}}, 1, nullptr, 0,
+                                 ST_FUS + 3 * i + 2, ST_NONE, 1, 1, 0, 0, nullptr, false, 2);
+      ConvProblem& hp = P.h_probs[ci];
+      if (hp.cout != 64 || hp.bn != 64) throw Error{FILM_ERR_UNSUPPORTED, "RGB-head epilogue expects a 64-channel N tile"};
+      hp.head_w4 = M.rgb_w;
+      hp.head_b4 = M.rgb_b;
+      hp.head_v = P.xout;
+      hp.crop_y = P.off_y;
+      hp.crop_x = P.off_x;
+      hp.crop_h = P.h;
+      hp.crop_w = P.w;
+      hp.crop_pitch = (int64_t)P.w * 3;
+    } else {
+      add_conv(P, "fusion_conv2@L" + std::to_string(i), 9.0 * nf * nf, M.fus_c2[i], {{f1, 0}}, 1, f2, 0, ST_FUS + 3 * i + 2,
+               i > 0 ? ST_FUS + 3 * (i - 1) : ST_NONE);
+    }
     if (i == kFusionLevels - 2) P.release(wf[i + 1]);   // the coarsest aligned level fed fusion_up only
     else P.release(net);                                // previous level's output, consumed by fusion_up
     P.release(wf[i]);
     P.release(up);
     P.release(f1);
     net = f2;
-    P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
+    if (f2) P.debug["fusion_net/" + std::to_string(i)] = DebugTensor{true, f2->hi, f2->lo, (int64_t)hh * ww, f2->C, 0, nf};
     P.debug["fusion_up/" + std::to_string(i)] = DebugTensor{true, up->hi, up->lo, (int64_t)hh * ww, up->C, 0, nf};
   }
   {
     const float *rw = M.rgb_w, *rb = M.rgb_b;
-    P.add_op(2, "rgb_head", [=](cudaStream_t st) {
-      return launch_rgb_head(net->hi, net->lo, net->C, pp->H, pp->W, rw, rb, pp->xout, (int64_t)pp->w * 3, pp->off_y,
-                             pp->off_x, pp->h, pp->w, st);
-    });
+    if (!(P.conv_impl == 0 && P.conv3x3_v2 && P.fuse_rgb_head && !keep_debug))
+      P.add_op(2, "rgb_head", [=](cudaStream_t st) {
+        return launch_rgb_head(net->hi, net->lo, net->C, pp->H, pp->W, rw, rb, pp->xout, (int64_t)pp->w * 3, pp->off_y,
+                               pp->off_x, pp->h, pp->w, st);
+      });
     P.debug["image"] = DebugTensor{false, P.xout, nullptr, (int64_t)h * w, 3, 0, 3};
     P.tok_end = P.new_token();
     P.signal_last(P.tok_end);
@@ -1125,6 +1159,8 @@ struct film_handle {
   int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
                          // persistent kernels (default), 3 also the 32-channel-chunk layers (experimental)
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
+  int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
+  int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
   uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
   size_t u8_bytes = 0;
   int num_sms = 148;
@@ -1194,13 +1230,13 @@ static void drop_plans(film_handle* h) {
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug);
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 4 + h->fuse_rgb_head * 2 + h->fe_conv0_tc);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p;
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0);
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2));
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1208,7 +1244,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     if (h->plans.empty()) throw;
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0);
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2));
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1293,6 +1329,8 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     FILM_CUDA(conv3x3_tc2_configure());
     if (const char* e2 = getenv("FILM_2CTA")) h->conv3x3_2cta = atoi(e2);
     if (const char* e3 = getenv("FILM_HALO")) h->conv3x3_halo = atoi(e3);
+    if (const char* e5 = getenv("FILM_FE0_TC")) h->fe_conv0_tc = atoi(e5) ? 1 : 0;
+    if (const char* e6 = getenv("FILM_RGB_FUSE")) h->fuse_rgb_head = atoi(e6) ? 1 : 0;
     if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
@@ -1356,6 +1394,8 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "conv3x3_halo") h->conv3x3_halo = value;
   else if (n == "onepass_mask") h->onepass_mask = (uint32_t)value & ((1u << ST_COUNT) - 1u);
   else if (n == "onepass_default") h->onepass_mask = kDefaultOnepassMask;
+  else if (n == "fe_conv0_tc") h->fe_conv0_tc = value ? 1 : 0;
+  else if (n == "fuse_rgb_head") h->fuse_rgb_head = value ? 1 : 0;
   else if (n == "clear_plans") drop_plans(h);
   else {
     h->err = "unknown option " + n;

@@ -149,6 +149,10 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
  *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes,
  *                   3 = also the 32-channel-chunk layers (experimental: not yet validated on hardware)
+ *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image
+ *                   (default), 1 = tensor-core kernel over a 32-channel-padded split image (comparison)
+ *   "fuse_rgb_head": 1 = the linear 1x1 RGB head and the crop run in the epilogue of the decoder's last 3x3 conv (default;
+ *                   the 64-channel activation is never stored), 0 = separate kernel
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)
  *   "clear_plans" : (any value) drop every cached (H, W, align) plan -- CUDA graph and activation arena --
  *                   after draining the handle's stream.  Plans are cached per shape and never evicted

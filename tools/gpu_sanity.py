@@ -21,7 +21,8 @@ dflt = eng0.get_option("onepass_default")
 eng0.close()
 ALL = (1 << nst) - 1
 variants = [{}, {"conv3x3_2cta": 0}, {"conv3x3_2cta": 2}, {"conv3x3_v2": 0}, {"conv3x3_halo": 0}, {"conv3x3_halo": 1},
-            {"conv3x3_halo": 3}, {"conv3x3_halo": 3, "conv3x3_2cta": 2}]
+            {"conv3x3_halo": 3}, {"conv3x3_halo": 3, "conv3x3_2cta": 2}, {"fe_conv0_tc": 1}, {"fuse_rgb_head": 0},
+            {"fe_conv0_tc": 1, "fuse_rgb_head": 0, "conv3x3_halo": 2}]
 bad = 0
 for var in variants:
     for mask in (0, dflt, ALL):
