@@ -221,10 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
     // Halo mode: one activation stage per chunk carries all nine taps; tap t = 3*dx + dy (the K order of the
     // packed weights) reads the box at byte offset (dy * 10 + dx) * 128, 8-row groups 1280 B apart.
-    auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag) {
+    auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag, auto res_tag) {
       constexpr bool kPartial = decltype(partial_tag)::value;
       constexpr bool kHalo = decltype(halo_tag)::value;
       constexpr bool kOne = decltype(one_tag)::value;   // single-pass product
+      constexpr bool kRes = decltype(res_tag)::value;   // weights resident in smem: no waits between the taps of a stage
+      constexpr int kWTapC = kWPlane * (kOne ? 1 : 2);
       constexpr int kStageTaps = kHalo ? 9 : 3;   // taps served by one activation stage
       constexpr int kSrcStages = kHalo ? 1 : 3;   // activation stages per chunk
       const int nab = nkb / kStageTaps;           // activation stages per tile
@@ -251,6 +253,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
           mbar_wait(tail + 8u * st, ra.phase);
           tc_fence_after();
           const uint32_t sa = a_base + st * kAStage;
+          if constexpr (kRes) {
+            // Resident weights: nothing to wait for inside the stage, so ONE elected lane issues all of its taps as
+            // straight-line code -- descriptors are a base plus compile-time offsets (the 14-bit address field
+            // cannot carry: smem offsets are < 256 KiB), ~2 instructions per MMA instead of ~90 per tap.
+            if (elect_one()) {
+              constexpr uint32_t kPx = KC * 2;   // bytes of one pixel row of the box
+              const uint64_t a0 = kHalo ? make_desc_sbo<KC>(sa, kHaloW * kPx) : make_desc_kc<KC>(sa);
+              const uint64_t lo_delta = (uint64_t)((kHalo ? kHaloPlane : kAPlane) >> 4);
+              const uint64_t row_delta = (uint64_t)(kRowStep >> 4);
+              const uint64_t w0 = make_desc_kc<KC>(w_base + kb * kWTapC);
+              const uint32_t first = (kb == 0) ? 0u : 1u;
+#pragma unroll
+              for (int t = 0; t < kStageTaps; ++t) {
+                const uint64_t a_hi = a0 + (kHalo ? (uint64_t)((((t % 3) * kHaloW + t / 3) * kPx) >> 4) : (uint64_t)t * row_delta);
+                const uint64_t a_lo = a_hi + lo_delta;
+                const uint64_t w_hi = w0 + (uint64_t)((t * kWTapC) >> 4), w_lo = w_hi + (uint64_t)(kWPlane >> 4);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  if (!kPartial || k < ksteps) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    const uint32_t accf = (t == 0 && k == 0) ? first : 1u;
+                    if constexpr (kOne) {
+                      umma(d_tmem, a_hi + adv, w_hi + adv, idesc, accf);
+                    } else if constexpr (kFused) {
+                      umma(d_tmem, a_hi + adv, w_hi + adv, idesc2, accf);  // N = 2*BN: [W_hi ; W_lo]
+                      umma(d_tmem, a_lo + adv, w_hi + adv, idesc, 1u);
+                    } else {
+                      umma(d_tmem, a_lo + adv, w_hi + adv, idesc, accf);
+                      umma(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                      umma(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+                    }
+                  }
+                }
+              }
+              umma_commit(tail + 8u * (kMaxRing + st));
+              if (ab == nab - 1) umma_commit(tail + 8u * (4 * kMaxRing + acc));
+            }
+            __syncwarp();
+            kb += kStageTaps;
+          } else
           for (int t = 0; t < kStageTaps; ++t, ++kb) {
             uint32_t sw;
             int ws = 0;
@@ -303,17 +345,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         }
       }
     };
-    auto run_pass = [&](auto one_tag) {
+    auto run_pass = [&](auto one_tag, auto res_tag) {
       if (halo) {
-        if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag);
-        else run_items(std::false_type{}, std::true_type{}, one_tag);
+        if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag, res_tag);
+        else run_items(std::false_type{}, std::true_type{}, one_tag, res_tag);
       } else {
-        if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag);
-        else run_items(std::false_type{}, std::false_type{}, one_tag);
+        if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag, res_tag);
+        else run_items(std::false_type{}, std::false_type{}, one_tag, res_tag);
       }
     };
-    if (one) run_pass(std::true_type{});
-    else run_pass(std::false_type{});
+    if (resident) {
+      if (one) run_pass(std::true_type{}, std::true_type{});
+      else run_pass(std::false_type{}, std::true_type{});
+    } else {
+      if (one) run_pass(std::true_type{}, std::false_type{});
+      else run_pass(std::false_type{}, std::false_type{});
+    }
   } else {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;              // TMEM lane quarter this warp may access

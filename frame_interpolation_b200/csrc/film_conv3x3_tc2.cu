@@ -243,10 +243,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // groups (one tile row each) 1280 B apart.
       bool any_partial = false;
       for (int s = 0; s < kMaxSrc; ++s) any_partial |= src_tab[2 * s] > 0 && src_tab[2 * kMaxSrc + s] < KC / 16;
-      auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag) {
+      auto run_items = [&](auto partial_tag, auto halo_tag, auto one_tag, auto res_tag) {
         constexpr bool kPartial = decltype(partial_tag)::value;
         constexpr bool kHalo = decltype(halo_tag)::value;
         constexpr bool kOne = decltype(one_tag)::value;   // single-pass product
+        constexpr bool kRes = decltype(res_tag)::value;   // weights resident: one elected lane issues a whole stage
+        constexpr int kWTapC = w_half_tap_bytes(BN, KC, kOne ? 1 : 2);
         constexpr int kStageTaps = kHalo ? 9 : 3;       // taps served by one activation stage
         constexpr int kSrcStages = kHalo ? 1 : 3;       // activation stages per chunk
         constexpr int kLoPlane = kHalo ? kHaloPlane : kAPlane;
@@ -275,6 +277,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             mbar_wait(a_full(st), ra.phase);
             tc_fence_after();
             const uint32_t sa = a_base + st * kStageBytes;
+            if constexpr (kRes) {
+              // resident weights: straight-line issue of all taps of the stage (see film_conv3x3_tc.cu)
+              if (elect_one()) {
+                constexpr uint32_t kPx = KC * 2;
+                const uint64_t a0 = kHalo ? make_desc_sbo<KC>(sa, kHaloW * kPx) : make_desc_kc<KC>(sa);
+                const uint64_t w0 = make_desc_kc<KC>(w_base + kb * kWTapC);
+                const uint32_t first = (kb == 0) ? 0u : 1u;
+#pragma unroll
+                for (int t = 0; t < kStageTaps; ++t) {
+                  const uint64_t a_hi = a0 + (uint64_t)((kHalo ? ((t % 3) * kHaloW + t / 3) * kPx : t * kRowStep) >> 4);
+                  const uint64_t a_lo = a_hi + (uint64_t)(kLoPlane >> 4);
+                  const uint64_t wt = w0 + (uint64_t)((t * kWTapC) >> 4);
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    if (!kPartial || k < ksteps) {
+                      const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                      const uint32_t accf = (t == 0 && k == 0) ? first : 1u;
+                      if constexpr (kOne) {
+                        umma_2sm(d_tmem, a_hi + adv, wt + adv, idesc, accf);          // halves of the W_hi rows
+                      } else if constexpr (kFused) {
+                        umma_2sm(d_tmem, a_hi + adv, wt + adv, idesc2, accf);         // X: W_hi (leader) / W_lo (peer)
+                        umma_2sm(d_tmem, a_lo + adv, wt + (uint64_t)(kWFull >> 4) + adv, idesc, 1u);   // Y: halves of W_hi
+                      } else {
+                        umma_2sm(d_tmem, a_lo + adv, wt + adv, idesc, accf);
+                        umma_2sm(d_tmem, a_hi + adv, wt + (uint64_t)(kWHalf >> 4) + adv, idesc, 1u);
+                        umma_2sm(d_tmem, a_hi + adv, wt + adv, idesc, 1u);
+                      }
+                    }
+                  }
+                }
+                umma_commit_2sm_mc(a_empty(st));
+                if (ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+              }
+              __syncwarp();
+              kb += kStageTaps;
+            } else
             for (int t = 0; t < kStageTaps; ++t, ++kb) {
               uint32_t sw;
               int ws = 0;
@@ -345,17 +383,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       };
-      auto run_pass = [&](auto one_tag) {
+      auto run_pass = [&](auto one_tag, auto res_tag) {
         if (halo) {
-          if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag);
-          else run_items(std::false_type{}, std::true_type{}, one_tag);
+          if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag, res_tag);
+          else run_items(std::false_type{}, std::true_type{}, one_tag, res_tag);
         } else {
-          if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag);
-          else run_items(std::false_type{}, std::false_type{}, one_tag);
+          if (any_partial) run_items(std::true_type{}, std::false_type{}, one_tag, res_tag);
+          else run_items(std::false_type{}, std::false_type{}, one_tag, res_tag);
         }
       };
-      if (one) run_pass(std::true_type{});
-      else run_pass(std::false_type{});
+      if (resident) {
+        if (one) run_pass(std::true_type{}, std::true_type{});
+        else run_pass(std::false_type{}, std::true_type{});
+      } else {
+        if (one) run_pass(std::true_type{}, std::false_type{});
+        else run_pass(std::false_type{}, std::false_type{});
+      }
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================
