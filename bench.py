@@ -476,7 +476,15 @@ def main():
               "achieved": gath_bytes / (gath_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
               "frac": gath_bytes / (gath_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms_per_step": gath_ms,
               "algorithmic_bytes_per_step": gath_bytes, "share_of_step": gath_ms / all_ms}
-    extra = extra_workloads(eng, world, rank, dev, dist if world > 1 else None) if not args.no_workloads else None
+    extra = None
+    if not args.no_workloads:
+        try:
+            extra = extra_workloads(eng, world, rank, dev, dist if world > 1 else None)
+        except Exception as exc:      # the headline line must survive a failure of the secondary workloads
+            import traceback
+            traceback.print_exc()
+            extra = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.synchronize()
     if args.op_table and rank == 0:
         with open(args.op_table, "w") as f:
             f.write("idx,category,name,ms,ref_flops,alg_bytes\n")
