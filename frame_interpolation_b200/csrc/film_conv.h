@@ -27,6 +27,9 @@ struct ConvSrc {
   int C;       // channel stride of the tensor (allocated channels)
   int c_off;   // first channel consumed
   int nchunk;  // number of K-block chunks consumed
+  int bswap;   // 1: this source is read with the batch index swapped (b -> B - 1 - b): the coarsest flow level pairs
+               // the features of image 0 with the UNWARPED features of image 1 and vice versa
+               // (pyramid_flow_estimator.py:148-149), which is the same tensor at the other batch index
   int ksteps;  // 16-channel k-steps issued per chunk (< kchunk/16 when the tail channels of every chunk are
                // zero padding, e.g. the 10-of-64 "side" source): skipping is exact.  Honoured by the persistent
                // 3x3 kernels; the generic kernel issues every k-step

@@ -56,7 +56,7 @@ __host__ __device__ constexpr int a_stage_bytes_h(int kc, int th, int tw, int ha
 constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
-constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table*/ + 1024 /*align*/ + 64;
+constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table: 16 ints*/ + 1024 /*align*/ + 64;
 
 __host__ __device__ inline int w_tap_bytes(int bn, int kc, int planes = 2) { return bn * kc * 2 * planes; }  // [BN x KC] hi (+ lo)
 
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       src_tab[2 * s] = s < nsrc ? prob->src[s].nchunk : 0;
       src_tab[2 * s + 1] = s < nsrc ? prob->src[s].c_off : 0;
       src_tab[2 * kMaxSrc + s] = s < nsrc ? prob->src[s].ksteps : 0;
+      src_tab[3 * kMaxSrc + s] = s < nsrc ? prob->src[s].bswap : 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       int kb = 0;
       for (int s = 0; s < nsrc; ++s) {
         const int nchunk = src_tab[2 * s], c_off = src_tab[2 * s + 1];
+        const int bs = src_tab[3 * kMaxSrc + s] ? prob->B - 1 - b : b;
         const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
         const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
         for (int ch = 0; ch < nchunk; ++ch) {
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             if (elect_one()) {
               const uint32_t sa = a_base + st * kAStage, bar = tail + 8u * st;
               mbar_expect_tx(bar, halo ? (uint32_t)(planes * kHaloBox) : (uint32_t)kAStage);
-              tma_load_4d(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
-              if (!one) tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+              tma_load_4d(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, bs);
+              if (!one) tma_load_4d(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, bs);
             }
             __syncwarp();
             ra.advance(NA);

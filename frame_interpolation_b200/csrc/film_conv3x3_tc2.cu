@@ -133,6 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       src_tab[2 * s] = s < nsrc ? prob->src[s].nchunk : 0;
       src_tab[2 * s + 1] = s < nsrc ? prob->src[s].c_off : 0;
       src_tab[2 * kMaxSrc + s] = s < nsrc ? prob->src[s].ksteps : 0;
+      src_tab[3 * kMaxSrc + s] = s < nsrc ? prob->src[s].bswap : 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,6 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int kb = 0;
       for (int s = 0; s < nsrc; ++s) {
         const int nchunk = src_tab[2 * s], c_off = src_tab[2 * s + 1];
+        const int bs = src_tab[3 * kMaxSrc + s] ? prob->B - 1 - b : b;
         const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
         const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
         for (int ch = 0; ch < nchunk; ++ch) {
@@ -191,12 +193,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               const uint32_t bar = map_to_cta(a_full(st), 0);
               if (halo) {
                 if (leader) mbar_expect_tx(a_full(st), 2u * planes * kHaloBox);   // planes x two CTAs
-                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
-                if (!one) tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, b);
+                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 - 1, y0 - 1, bs);
+                if (!one) tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, bs);
               } else {
                 if (leader) mbar_expect_tx(a_full(st), 2u * planes * kAPlane);
-                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
-                if (!one) tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, b);
+                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, bs);
+                if (!one) tma_load_4d_2sm(sa + kAPlane, tm_lo, bar, c_off + ch * KC, x0 + dx - 1, y0 - 1, bs);
               }
             }
             __syncwarp();

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
     int kb = 0;
     for (int s = 0; s < nsrc; ++s) {
       const int nchunk = prob->src[s].nchunk, c_off = prob->src[s].c_off;
+      const int bs = prob->src[s].bswap ? prob->B - 1 - b : b;
       const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
       const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
       for (int ch = 0; ch < nchunk; ++ch) {
@@ -134,10 +135,10 @@ __global__ void __launch_bounds__(kNumThreads, TcCfg<BN, KC>::kMinBlocks) k_conv
             const uint32_t sa = base + stage * Cfg::kStageBytes;
             mbar_expect_tx(full_bar(stage), one ? (uint32_t)(kABytes + Cfg::kWBytes) : (uint32_t)Cfg::kStageBytes);
             const int cc = c_off + ch * KC;
-            tma_load_4d(sa, tm_hi, full_bar(stage), cc, xx, yy, b);
+            tma_load_4d(sa, tm_hi, full_bar(stage), cc, xx, yy, bs);
             tma_load_2d(sa + 2 * kABytes, tm_w_hi, full_bar(stage), kb * KC, n0);
             if (!one) {
-              tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, b);
+              tma_load_4d(sa + kABytes, tm_lo, full_bar(stage), cc, xx, yy, bs);
               tma_load_2d(sa + 2 * kABytes + Cfg::kWBytes, tm_w_lo, full_bar(stage), kb * KC, n0);
             }
           }

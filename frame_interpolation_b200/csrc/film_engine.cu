@@ -448,6 +448,7 @@ struct SplitBuf {
 struct SrcRef {
   const SplitBuf* buf;
   int c_off;
+  int bswap = 0;  // read with the batch index swapped (ConvSrc::bswap)
 };
 struct DebugTensor {
   bool split;
@@ -625,6 +626,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     cp.src[s].c_off = sources[s].c_off;
     cp.src[s].nchunk = pc.src_chunks[s];
     cp.src[s].ksteps = pc.src_ksteps[s];
+    cp.src[s].bswap = sources[s].bswap;
     if (sources[s].c_off + pc.src_chunks[s] * kc > b->C) throw Error{FILM_ERR_ARG, "conv source channel overrun"};
     make_act_map(&cp.tm_a_hi[s], b->hi, b->B, b->H, b->W, b->C, box_h, box_w, kc);
     make_act_map(&cp.tm_a_lo[s], b->lo, b->B, b->H, b->W, b->C, box_h, box_w, kc);
@@ -888,18 +890,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     const SplitBuf* second;  // second operand of concat(a, b)
     float* vup = nullptr;
     if (l == kLevels - 1) {
-      // coarsest level: b = features of the other image, unwarped.  Built as a batch-swapped copy.
-      SplitBuf* sw = P.split(2, hh, ww, C);
-      const SplitBuf* f = feat[l];
-      const int64_t half = (int64_t)hh * ww * C * (int64_t)sizeof(sp_t);
-      P.add_op(2, "flow_swap@L" + std::to_string(l), [=](cudaStream_t st) {
-        cudaError_t e;
-        if ((e = cudaMemcpyAsync(sw->hi, (const char*)f->hi + half, half, cudaMemcpyDeviceToDevice, st))) return e;
-        if ((e = cudaMemcpyAsync((char*)sw->hi + half, f->hi, half, cudaMemcpyDeviceToDevice, st))) return e;
-        if ((e = cudaMemcpyAsync(sw->lo, (const char*)f->lo + half, half, cudaMemcpyDeviceToDevice, st))) return e;
-        return cudaMemcpyAsync((char*)sw->lo + half, f->lo, half, cudaMemcpyDeviceToDevice, st);
-      });
-      second = sw;
+      // coarsest level: b = features of the other image, unwarped = the same tensor read at the other batch
+      // index (ConvSrc::bswap: a TMA coordinate, no copy)
+      second = nullptr;
     } else {
       SplitBuf* warped = P.split(2, hh, ww, C);
       vup = P.alloc<float>((int64_t)2 * hh * ww * 2);
@@ -930,8 +923,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);
     const std::string lt = "@L" + std::to_string(l);
-    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], {{feat[l], 0}, {second, 0}}, 1, c0, 0, ST_FLOW_L0 + l,
-             ST_FLOW_L0 + l);
+    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0],
+             {{feat[l], 0}, second ? SrcRef{second, 0} : SrcRef{feat[l], 0, 1}}, 1, c0, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l, ST_NONE);
     if (P.conv_impl == 1) {

@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvProblem* __restrict
       for (int t = 0; t < P.ntaps; ++t, ++kb) {
         const int yy = py + P.tap_dy[t], xx = px + P.tap_dx[t];
         const bool ok = pm_ok && yy >= 0 && yy < P.H && xx >= 0 && xx < P.W;
-        const int64_t abase = (((int64_t)pb * P.H + yy) * P.W + xx) * S.C + S.c_off + ch * KC;
+        const int64_t abase = (((int64_t)(S.bswap ? P.B - 1 - pb : pb) * P.H + yy) * P.W + xx) * S.C + S.c_off + ch * KC;
         for (int k16 = 0; k16 < KC; k16 += 16) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
