@@ -448,7 +448,7 @@ struct SplitBuf {
 struct SrcRef {
   const SplitBuf* buf;
   int c_off;
-  int bswap = 0;  // read with the batch index swapped (ConvSrc::bswap)
+  int bswap;  // read with the batch index swapped (ConvSrc::bswap); 0 when omitted from a braced initialiser
 };
 struct DebugTensor {
   bool split;
@@ -923,8 +923,13 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     SplitBuf* c1 = P.split(2, hh, ww, cpad);
     SplitBuf* c2 = P.split(2, hh, ww, cpad);
     const std::string lt = "@L" + std::to_string(l);
-    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0],
-             {{feat[l], 0}, second ? SrcRef{second, 0} : SrcRef{feat[l], 0, 1}}, 1, c0, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
+    std::vector<SrcRef> flow_src(2);
+    flow_src[0].buf = feat[l];
+    flow_src[0].c_off = 0;
+    flow_src[1].buf = second ? second : feat[l];
+    flow_src[1].c_off = 0;
+    flow_src[1].bswap = second ? 0 : 1;
+    add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], flow_src, 1, c0, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l, ST_NONE);
     if (P.conv_impl == 1) {
