@@ -29,4 +29,7 @@ timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --sectio
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_tc2 -c 20 -f -o gpurun_out/${T}_pair python tools/profile_step.py 0 > gpurun_out/${T}_ncu_pair.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_conv3x3_tc<" -c 30 -f -o gpurun_out/${T}_single python tools/profile_step.py 0 > gpurun_out/${T}_ncu_single.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_flow_warp|k_fusion_warp|k_conv_tc" -c 24 -f -o gpurun_out/${T}_misc python tools/profile_step.py 0 > gpurun_out/${T}_ncu_misc.log 2>&1
+# memcheck of one small network call (arena reuse, lo-plane skipping, fused epilogues): any out-of-bounds access shows up here
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/${T}_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a gpurun_out/${T}_memcheck.log
+tail -4 gpurun_out/${T}_memcheck.log
 ls -la gpurun_out | grep ${T}
