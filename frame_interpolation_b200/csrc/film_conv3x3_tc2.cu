@@ -72,7 +72,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   constexpr int kRowStep = kTileW * KC * 2;
   constexpr int kHaloBox = halo_box_bytes(KC), kHaloPlane = halo_plane_bytes(KC), kHaloStage = halo_stage_bytes(KC);
   constexpr uint32_t kAccCols = kFused ? 2 * BN : BN;
-  constexpr uint32_t kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
+  // double-buffered accumulators; N tiles <= 128 reserve two SETS per buffer for the dual-item mode
+  constexpr uint32_t kTmemCols = (BN <= 128) ? 4 * kAccCols : 2 * kAccCols;
+  static_assert(kTmemCols >= 32 && kTmemCols <= 512, "TMEM budget");
 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -94,6 +96,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int n_nt = (cout + BN - 1) / BN;
   const int nitems = prob->B * pairs_per_img * n_nt;   // work items: (tile pair, N tile), N fastest
   const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+  // dual-item mode (host guarantees: streamed weights, wide halo, one N tile, BN <= 128, NA >= 2): a "super item" is
+  // two consecutive spatial items sharing every weight tap
+  const bool dual = prob->dual != 0;
+  const int sub_n = dual ? 2 : 1;
+  const int nsuper = dual ? (nitems + 1) / 2 : nitems;
   int nkb = 0;
   for (int s = 0; s < nsrc; ++s) nkb += prob->src[s].nchunk * 9;
 
@@ -172,6 +179,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
     RingPos ra, rw;   // activation / weight ring positions
+    if (dual) {
+      // chunk by chunk: the halo boxes of BOTH sub-items, then the nine weight taps they share
+      for (int sit = item0; sit < nsuper; sit += item_step) {
+        const int nsub = (2 * sit + 1 < nitems) ? 2 : 1;
+        int kb = 0;
+        for (int s = 0; s < nsrc; ++s) {
+          const int nchunk = src_tab[2 * s], c_off = src_tab[2 * s + 1];
+          const bool swap = src_tab[3 * kMaxSrc + s] != 0;
+          const CUtensorMap* tm_hi = &prob->tm_a_hi[s];
+          const CUtensorMap* tm_lo = &prob->tm_a_lo[s];
+          for (int ch = 0; ch < nchunk; ++ch) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const int sp = 2 * sit + sub;   // n_nt == 1
+              const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
+              const int y0 = (2 * (rem / tiles_x) + (int)rank) * kTileH, x0 = (rem % tiles_x) * kTileW;
+              const int bs = swap ? prob->B - 1 - b : b;
+              const int st = ra.stage;
+              mbar_wait(a_empty(st), ra.phase ^ 1u);
+              if (elect_one()) {
+                const uint32_t sa = a_base + st * a_stage;
+                const uint32_t bar = map_to_cta(a_full(st), 0);
+                if (leader) mbar_expect_tx(a_full(st), 2u * planes * kHaloBox);
+                tma_load_4d_2sm(sa, tm_hi, bar, c_off + ch * KC, x0 - 1, y0 - 1, bs);
+                if (!one) tma_load_4d_2sm(sa + kHaloPlane, tm_lo, bar, c_off + ch * KC, x0 - 1, y0 - 1, bs);
+              }
+              __syncwarp();
+              ra.advance(NA);
+            }
+            for (int t = 0; t < 9; ++t, ++kb) {
+              const int ws = rw.stage;
+              mbar_wait(w_empty(ws), rw.phase ^ 1u);
+              if (elect_one()) {
+                const uint32_t sw = w_base + ws * kWTap;
+                const uint32_t bar = map_to_cta(w_full(ws), 0);
+                if (leader) mbar_expect_tx(w_full(ws), 2u * kWTap);
+                if (one) {
+                  tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n_half);
+                } else if constexpr (kFused) {
+                  tma_load_2d_2sm(sw, leader ? tm_w_full_hi : tm_w_full_lo, bar, kb * KC, 0);
+                  tma_load_2d_2sm(sw + kWFull, tm_w_hi, bar, kb * KC, n_half);
+                } else {
+                  tma_load_2d_2sm(sw, tm_w_hi, bar, kb * KC, n_half);
+                  tma_load_2d_2sm(sw + kWHalf, tm_w_lo, bar, kb * KC, n_half);
+                }
+              }
+              __syncwarp();
+              rw.advance(NW);
+            }
+          }
+        }
+      }
+    } else
     for (int item = item0; item < nitems; item += item_step) {
       const int sp = item / n_nt, n0 = (item % n_nt) * BN;
       const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
@@ -385,6 +444,82 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       };
+      // dual-item mode: per chunk wait for the halo boxes of both sub-items, then every weight tap is used twice
+      auto run_items_dual = [&](auto partial_tag, auto one_tag) {
+        constexpr bool kPartial = decltype(partial_tag)::value;
+        constexpr bool kOne = decltype(one_tag)::value;
+        constexpr int kStageBytes = (kOne ? 1 : 2) * kHaloPlane;
+        constexpr uint32_t kPx = KC * 2;
+        const int nab = nkb / 9;
+        RingPos ra, rw;
+        uint32_t it = 0;
+        for (int sit = item0; sit < nsuper; sit += item_step, ++it) {
+          const int nsub = (2 * sit + 1 < nitems) ? 2 : 1;
+          const uint32_t acc = it & 1u;
+          mbar_wait(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          int kb = 0;
+          [[maybe_unused]] int src_i = 0, src_left = src_tab[0];
+          for (int ab = 0; ab < nab; ++ab) {
+            [[maybe_unused]] int ksteps = KC / 16;
+            if constexpr (kPartial) {
+              while (src_left == 0) {
+                ++src_i;
+                src_left = src_tab[2 * src_i];
+              }
+              --src_left;
+              ksteps = src_tab[2 * kMaxSrc + src_i];
+            }
+            int st2[2] = {0, 0};
+            for (int sub = 0; sub < nsub; ++sub) {
+              st2[sub] = ra.stage;
+              mbar_wait(a_full(ra.stage), ra.phase);
+              ra.advance(NA);
+            }
+            tc_fence_after();
+            for (int t = 0; t < 9; ++t, ++kb) {
+              const int ws = rw.stage;
+              mbar_wait(w_full(ws), rw.phase);
+              tc_fence_after();
+              const uint32_t sw = w_base + ws * kWTap;
+              if (elect_one()) {
+                const uint32_t off = (uint32_t)((t % 3) * kHaloW + t / 3) * kPx;
+                const uint32_t first = (kb == 0) ? 0u : 1u;
+                for (int sub = 0; sub < nsub; ++sub) {
+                  const uint32_t sa = a_base + st2[sub] * kStageBytes;
+                  const uint32_t d_tmem = tmem_base + (acc * 2 + sub) * kAccCols;
+                  const uint64_t a_hi = make_desc_sbo<KC>(sa + off, kHaloW * kPx);
+                  const uint64_t a_lo = make_desc_sbo<KC>(sa + kHaloPlane + off, kHaloW * kPx);
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    if (!kPartial || k < ksteps) {
+                      const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                      const uint32_t accf = k == 0 ? first : 1u;
+                      if constexpr (kOne) {
+                        umma_2sm(d_tmem, a_hi + adv, make_desc_kc<KC>(sw) + adv, idesc, accf);
+                      } else if constexpr (kFused) {
+                        umma_2sm(d_tmem, a_hi + adv, make_desc_kc<KC>(sw) + adv, idesc2, accf);
+                        umma_2sm(d_tmem, a_lo + adv, make_desc_kc<KC>(sw + kWFull) + adv, idesc, 1u);
+                      } else {
+                        umma_2sm(d_tmem, a_lo + adv, make_desc_kc<KC>(sw) + adv, idesc, accf);
+                        umma_2sm(d_tmem, a_hi + adv, make_desc_kc<KC>(sw + kWHalf) + adv, idesc, 1u);
+                        umma_2sm(d_tmem, a_hi + adv, make_desc_kc<KC>(sw) + adv, idesc, 1u);
+                      }
+                    }
+                  }
+                }
+                umma_commit_2sm_mc(w_empty(ws));
+                if (t == 8) {
+                  for (int sub = 0; sub < nsub; ++sub) umma_commit_2sm_mc(a_empty(st2[sub]));
+                  if (ab == nab - 1) umma_commit_2sm_mc(t_full(acc));
+                }
+              }
+              __syncwarp();
+              rw.advance(NW);
+            }
+          }
+        }
+      };
       auto run_pass = [&](auto one_tag, auto res_tag) {
         if (halo) {
           if (any_partial) run_items(std::true_type{}, std::true_type{}, one_tag, res_tag);
@@ -394,7 +529,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           else run_items(std::false_type{}, std::false_type{}, one_tag, res_tag);
         }
       };
-      if (resident) {
+      if (dual) {
+        if (one) {
+          if (any_partial) run_items_dual(std::true_type{}, std::true_type{});
+          else run_items_dual(std::false_type{}, std::true_type{});
+        } else {
+          if (any_partial) run_items_dual(std::true_type{}, std::false_type{});
+          else run_items_dual(std::false_type{}, std::false_type{});
+        }
+      } else if (resident) {
         if (one) run_pass(std::true_type{}, std::true_type{});
         else run_pass(std::false_type{}, std::true_type{});
       } else {
@@ -418,8 +561,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const bool lo_skip = prob->out_lo_skip != 0;
     const uint32_t t_empty_leader0 = map_to_cta(t_empty(0), 0), t_empty_leader1 = map_to_cta(t_empty(1), 0);
     uint32_t it = 0;
-    for (int item = item0; item < nitems; item += item_step, ++it) {
+    for (int sit = item0; sit < nsuper; sit += item_step, ++it) {
       const uint32_t acc = it & 1u;
+      mbar_wait(t_full(acc), (it >> 1) & 1u);
+      tc_fence_after();
+      const int nsub = (dual && 2 * sit + 1 < nitems) ? 2 : 1;
+     for (int sub = 0; sub < nsub; ++sub) {
+      const int item = dual ? 2 * sit + sub : sit;
       const int sp = item / n_nt, n0 = (item % n_nt) * BN;
       const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
       const int py = (2 * (rem / tiles_x) + (int)rank) * kTileH + r / kTileW, px = (rem % tiles_x) * kTileW + r % kTileW;
@@ -427,9 +575,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int64_t opix = ((int64_t)b * out_H + py) * out_W + px;
       sp_t* oh = out_hi + opix * out_C + out_c_off + n0;
       sp_t* ol = out_lo + opix * out_C + out_c_off + n0;
-      mbar_wait(t_full(acc), (it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + (acc * sub_n + sub) * kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = half; cc < BN / 16; cc += 2) {
         if (n0 + cc * 16 >= cout) break;
@@ -469,6 +615,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
+     }  // sub-items
       // this CTA's half of the accumulator is drained: tell the leader's MMA warp
       tc_fence_before();
       __syncwarp();
@@ -525,7 +672,25 @@ bool conv3x3_tc2_plan(ConvProblem& h, int num_sms) {
     if (h.v2_nw < 2) return false;
   }
   const int pairs_y = (h.tiles_y + 1) / 2;
-  const int nitems = h.B * pairs_y * h.tiles_x * ((h.cout + bn - 1) / bn);
+  const int n_nt = (h.cout + bn - 1) / bn;
+  int nitems = h.B * pairs_y * h.tiles_x * n_nt;
+  // dual-item mode (the engine sets h.dual = 1 to ALLOW it): streamed weights, wide halo, one N tile, two accumulator
+  // sets in TMEM (BN <= 128) and at least one activation stage per sub-item with two weight stages next to them
+  if (h.dual) {
+    bool ok = !h.v2_resident && h.halo && n_nt == 1 && bn <= 128 && nitems >= 4 * (num_sms / 2);
+    if (ok) {
+      int na = 4;
+      if (na * a_stage + 2 * wtap + kFixedBytes > kSmemLimit) na = 2;
+      ok = na * a_stage + 2 * wtap + kFixedBytes <= kSmemLimit;
+      if (ok) {
+        h.v2_na = na;
+        int nw = (kSmemLimit - kFixedBytes - na * a_stage) / wtap;
+        h.v2_nw = nw > kMaxRing ? kMaxRing : nw;
+        nitems = (nitems + 1) / 2;
+      }
+    }
+    h.dual = ok ? 1 : 0;
+  }
   int grid = 2 * nitems;
   const int max_grid = num_sms & ~1;
   h.v2_grid = grid < max_grid ? grid : max_grid;

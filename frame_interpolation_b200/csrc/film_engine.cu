@@ -467,6 +467,7 @@ struct Plan {
   uint32_t onepass_mask = 0;  // precision plan: stages on the single-pass product
   int fe_conv0_tc = 0;        // 1: cfeat_conv_0 on the tensor cores (32-channel-padded image), 0: fp32 FMA kernel
   int fuse_rgb_head = 1;      // RGB head + crop in the epilogue of the decoder's last conv
+  int conv3x3_dual = 0;       // CTA-pair kernel: two spatial items per streamed weight pass
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -693,6 +694,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   if (want_pair && (!cp.v2_resident || cp.ktot / cp.kchunk >= 18 || P.conv3x3_2cta >= 2)) {
     ConvProblem alt = cp;
     alt.halo = halo_ok >= 1;
+    alt.dual = P.conv3x3_dual;
     if (conv3x3_tc2_plan(alt, P.num_sms)) {
       cp = alt;
       pair = true;
@@ -732,6 +734,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   Plan& P = *pl;
   P.fe_conv0_tc = fe_conv0_tc & 1;
   P.fuse_rgb_head = (fe_conv0_tc & 2) ? 0 : 1;
+  P.conv3x3_dual = (fe_conv0_tc & 4) ? 1 : 0;
   P.onepass_mask = onepass_mask;
   P.reuse = !keep_debug && !use_lanes;
   P.h = h;
@@ -1159,6 +1162,7 @@ struct film_handle {
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
   int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
+  int conv3x3_dual = 0;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass
   uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
   size_t u8_bytes = 0;
   int num_sms = 148;
@@ -1228,13 +1232,13 @@ static void drop_plans(film_handle* h) {
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 4 + h->fuse_rgb_head * 2 + h->fe_conv0_tc);
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 8 + h->conv3x3_dual * 4 + h->fuse_rgb_head * 2 + h->fe_conv0_tc);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p;
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2));
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0));
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1242,7 +1246,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     if (h->plans.empty()) throw;
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2));
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0));
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1329,6 +1333,7 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     if (const char* e3 = getenv("FILM_HALO")) h->conv3x3_halo = atoi(e3);
     if (const char* e5 = getenv("FILM_FE0_TC")) h->fe_conv0_tc = atoi(e5) ? 1 : 0;
     if (const char* e6 = getenv("FILM_RGB_FUSE")) h->fuse_rgb_head = atoi(e6) ? 1 : 0;
+    if (const char* e7 = getenv("FILM_DUAL")) h->conv3x3_dual = atoi(e7) ? 1 : 0;
     if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
@@ -1394,6 +1399,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "onepass_default") h->onepass_mask = kDefaultOnepassMask;
   else if (n == "fe_conv0_tc") h->fe_conv0_tc = value ? 1 : 0;
   else if (n == "fuse_rgb_head") h->fuse_rgb_head = value ? 1 : 0;
+  else if (n == "conv3x3_dual") h->conv3x3_dual = value ? 1 : 0;
   else if (n == "clear_plans") drop_plans(h);
   else {
     h->err = "unknown option " + n;

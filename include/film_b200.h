@@ -151,6 +151,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   3 = also the 32-channel-chunk layers (experimental: not yet validated on hardware)
  *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image
  *                   (default), 1 = tensor-core kernel over a 32-channel-padded split image (comparison)
+ *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes
+ *                   resident, two accumulator sets in TMEM): halves the weight bytes pulled from L2 per item on the
+ *                   layers that are L2->SM ingest bound; 0 = one item per weight pass
  *   "fuse_rgb_head": 1 = the linear 1x1 RGB head and the crop run in the epilogue of the decoder's last 3x3 conv (default;
  *                   the 64-channel activation is never stored), 0 = separate kernel
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)

@@ -10,7 +10,7 @@ torch.set_num_threads(16)
 wpath = weights.ensure_synthetic_file()
 orc = OracleInterpolator(weights.load(wpath), align=64)
 dt = np.full((1,), 0.5, np.float32)
-cases = [(256, 320, 13), (120, 180, 3)]
+cases = [(256, 320, 13), (120, 180, 3), (576, 1024, 4)]   # the last one is large enough for the dual-item pair kernel
 refs = {}
 for h, w, s in cases:
     x0, x1 = synthetic.frame_pair(h, w, seed=s, n_waves=8)
@@ -22,7 +22,8 @@ eng0.close()
 ALL = (1 << nst) - 1
 variants = [{}, {"conv3x3_2cta": 0}, {"conv3x3_2cta": 2}, {"conv3x3_v2": 0}, {"conv3x3_halo": 0}, {"conv3x3_halo": 1},
             {"conv3x3_halo": 3}, {"conv3x3_halo": 3, "conv3x3_2cta": 2}, {"fe_conv0_tc": 1}, {"fuse_rgb_head": 0},
-            {"fe_conv0_tc": 1, "fuse_rgb_head": 0, "conv3x3_halo": 2}]
+            {"fe_conv0_tc": 1, "fuse_rgb_head": 0, "conv3x3_halo": 2}, {"conv3x3_dual": 1},
+            {"conv3x3_dual": 1, "conv3x3_2cta": 2}]
 bad = 0
 for var in variants:
     for mask in (0, dflt, ALL):
