@@ -92,6 +92,26 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert b"sm_100a" in lib.film_version()
 
 
+def test_precision_plan_stage_table(built_lib):
+    """The stages of the precision plan are part of the C ABI (bit positions of option "onepass_mask"): 7 feature-extractor
+    groups, 7 flow levels, 4 fusion levels x 3 convs, in that order; readable without a GPU."""
+    import ctypes
+    lib = ctypes.CDLL(built_lib)
+    n = lib.film_stage_count()
+    assert n == 26
+    names = []
+    for i in range(n):
+        buf = ctypes.create_string_buffer(32)
+        assert lib.film_stage_name(i, buf, 32) == 0
+        names.append(buf.value.decode())
+    assert names[:7] == ["fe_i0_k01", "fe_i0_k23", "fe_i0_k45", "fe_i0_k67", "fe_i1", "fe_i2", "fe_i3p"]
+    assert names[7:14] == [f"flow_L{l}" for l in range(7)]
+    assert names[14:] == [f"fus{l}_c{c}" for l in range(4) for c in range(3)]
+    buf = ctypes.create_string_buffer(4)
+    assert lib.film_stage_name(n, buf, 4) != 0 and lib.film_stage_name(-1, buf, 4) != 0      # out of range -> status 1
+    assert lib.film_stage_name(0, buf, 4) == 0 and buf.value == b"fe_"                      # truncated, NUL-terminated
+
+
 def test_engine_fails_loudly_without_gpu(built_lib):
     import torch
     if torch.cuda.is_available():
