@@ -98,6 +98,8 @@ struct alignas(64) ConvProblem {
                           // (11-bit fp16 operands, fp32 accumulate; only the hi planes of the activations and
                           // weights are loaded).  Chosen per call site by the engine's precision plan
                           // (film_engine.cu).
+  int straight;           // persistent kernels, resident weights: 1 = one elected lane issues a whole activation stage as
+                          // straight-line code (default), 0 = per-tap issue loop
   int dual;               // CTA-pair kernel, streamed weights, wide halo: 1 = every weight tap pulled from L2 serves TWO
                           // spatial work items (their activation stages are resident together, two accumulator
                           // sets in TMEM): halves the weight bytes per item where the layer is L2->SM ingest bound

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
         else run_items(std::false_type{}, std::false_type{}, one_tag, res_tag);
       }
     };
-    if (resident) {
+    if (resident && prob->straight) {
       if (one) run_pass(std::true_type{}, std::true_type{});
       else run_pass(std::false_type{}, std::true_type{});
     } else {

@@ -537,7 +537,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           if (any_partial) run_items_dual(std::true_type{}, std::false_type{});
           else run_items_dual(std::false_type{}, std::false_type{});
         }
-      } else if (resident) {
+      } else if (resident && prob->straight) {
         if (one) run_pass(std::true_type{}, std::true_type{});
         else run_pass(std::false_type{}, std::true_type{});
       } else {

@@ -468,6 +468,8 @@ struct Plan {
   int fe_conv0_tc = 0;        // 1: cfeat_conv_0 on the tensor cores (32-channel-padded image), 0: fp32 FMA kernel
   int fuse_rgb_head = 1;      // RGB head + crop in the epilogue of the decoder's last conv
   int conv3x3_dual = 0;       // CTA-pair kernel: two spatial items per streamed weight pass
+  int plane_skip = 1;         // lo planes that no consumer reads are neither gathered nor written
+  int mma_straight = 1;       // straight-line MMA issue for resident weights
   std::vector<void*> allocs;
   int64_t arena_bytes = 0;
   std::vector<ConvProblem> h_probs;
@@ -584,7 +586,8 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   ConvProblem cp;
   memset(&cp, 0, sizeof(cp));
   cp.passes = (stage >= 0 && P.conv_impl == 0 && ((P.onepass_mask >> stage) & 1u)) ? 1 : 3;
-  cp.out_lo_skip = (consumer >= 0 && P.conv_impl == 0 && !pool_out && ((P.onepass_mask >> consumer) & 1u)) ? 1 : 0;
+  cp.out_lo_skip = (consumer >= 0 && P.conv_impl == 0 && !pool_out && P.plane_skip && ((P.onepass_mask >> consumer) & 1u)) ? 1 : 0;
+  cp.straight = P.mma_straight;
   const SplitBuf* s0 = sources[0].buf;
   cp.nsrc = (int)sources.size();
   if (cp.nsrc != (int)pc.src_chunks.size()) throw Error{FILM_ERR_WEIGHTS, "source count mismatch"};
@@ -735,6 +738,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.fe_conv0_tc = fe_conv0_tc & 1;
   P.fuse_rgb_head = (fe_conv0_tc & 2) ? 0 : 1;
   P.conv3x3_dual = (fe_conv0_tc & 4) ? 1 : 0;
+  P.plane_skip = (fe_conv0_tc & 8) ? 0 : 1;
+  P.mma_straight = (fe_conv0_tc & 16) ? 0 : 1;
+  if (fe_conv0_tc & 32) P.reuse = false;
   P.onepass_mask = onepass_mask;
   P.reuse = !keep_debug && !use_lanes;
   P.h = h;
@@ -809,7 +815,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         const int hh = Hs[r], ww = Ws[r];
         const float *w0 = M.conv0_w, *b0 = M.conv0_b;
         sp_t *oh = t1->hi, *ol = t1->lo;
-        const bool lo_skip = (P.onepass_mask >> fe_stage(i, 1)) & 1u;   // only reader: cfeat_conv_1 of this sub-tree
+        const bool lo_skip = P.plane_skip && ((P.onepass_mask >> fe_stage(i, 1)) & 1u);   // only reader: cfeat_conv_1 of this sub-tree
         P.add_op(2, "fe_conv0@L" + std::to_string(r),
                  [=](cudaStream_t st) { return launch_fe_conv0(im, 2, hh, ww, w0, b0, oh, ol, lo_skip, st); },
                  2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 * 4 + 64 * (lo_skip ? 2.0 : 4.0)));
@@ -904,7 +910,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       const int hc = Hs[l + 1], wc = Ws[l + 1];
       float* vu = vup;
       // the warped features feed flow_conv0 of this level only: a single-pass consumer reads hi planes alone
-      const bool hi_only = P.conv_impl == 0 && ((P.onepass_mask >> (ST_FLOW_L0 + l)) & 1u);
+      const bool hi_only = P.conv_impl == 0 && P.plane_skip && ((P.onepass_mask >> (ST_FLOW_L0 + l)) & 1u);
       const double wbytes = 2.0 * hh * ww * (double)C * (hi_only ? 4.0 : 8.0);
       P.add_op(1, "flow_warp@L" + std::to_string(l), [=](cudaStream_t st) {
         return launch_flow_warp(vprev, hc, wc, f->hi, f->lo, hh, ww, C, vu, warped->hi, warped->lo, hi_only, st);
@@ -983,7 +989,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     const SplitBuf *f = feat[l], *o = wf[l], *sd = side[l];
     // consumers of the warped level: fusion_conv1 of the level (fusion_up of level 3 for the coarsest one)
     const int cons = l == kFusionLevels - 1 ? ST_FUS + 3 * (l - 1) : ST_FUS + 3 * l + 1;
-    const bool hi_only = P.conv_impl == 0 && ((P.onepass_mask >> cons) & 1u);
+    const bool hi_only = P.conv_impl == 0 && P.plane_skip && ((P.onepass_mask >> cons) & 1u);
     const double wbytes = 2.0 * hh * ww * (double)C * (hi_only ? 4.0 : 8.0);
     P.add_op(1, "fusion_warp@L" + std::to_string(l), [=](cudaStream_t st) {
       return launch_fusion_warp(vv, f->hi, f->lo, hh, ww, C, o->hi, o->lo, hi_only, st);
@@ -1163,6 +1169,7 @@ struct film_handle {
   int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
   int conv3x3_dual = 0;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass
+  int plane_skip = 1, mma_straight = 1, arena_reuse = 1;   // round-2 optimisations, individually switchable (A/B, bisecting)
   uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
   size_t u8_bytes = 0;
   int num_sms = 148;
@@ -1232,13 +1239,15 @@ static void drop_plans(film_handle* h) {
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 8 + h->conv3x3_dual * 4 + h->fuse_rgb_head * 2 + h->fe_conv0_tc);
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 64 + h->arena_reuse * 32 + h->mma_straight * 16 + h->plane_skip * 8 + h->conv3x3_dual * 4 +
+               h->fuse_rgb_head * 2 + h->fe_conv0_tc);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
   std::unique_ptr<Plan> p;
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0));
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32));
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1246,7 +1255,8 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     if (h->plans.empty()) throw;
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
-                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0));
+                   h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32));
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1334,6 +1344,9 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     if (const char* e5 = getenv("FILM_FE0_TC")) h->fe_conv0_tc = atoi(e5) ? 1 : 0;
     if (const char* e6 = getenv("FILM_RGB_FUSE")) h->fuse_rgb_head = atoi(e6) ? 1 : 0;
     if (const char* e7 = getenv("FILM_DUAL")) h->conv3x3_dual = atoi(e7) ? 1 : 0;
+    if (const char* e8 = getenv("FILM_PLANE_SKIP")) h->plane_skip = atoi(e8) ? 1 : 0;
+    if (const char* e9 = getenv("FILM_STRAIGHT")) h->mma_straight = atoi(e9) ? 1 : 0;
+    if (const char* e10 = getenv("FILM_ARENA_REUSE")) h->arena_reuse = atoi(e10) ? 1 : 0;
     if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
     h->num_sms = prop.multiProcessorCount;
     WeightMap w = read_weight_file(weights_path);
@@ -1400,6 +1413,9 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "fe_conv0_tc") h->fe_conv0_tc = value ? 1 : 0;
   else if (n == "fuse_rgb_head") h->fuse_rgb_head = value ? 1 : 0;
   else if (n == "conv3x3_dual") h->conv3x3_dual = value ? 1 : 0;
+  else if (n == "plane_skip") h->plane_skip = value ? 1 : 0;
+  else if (n == "mma_straight") h->mma_straight = value ? 1 : 0;
+  else if (n == "arena_reuse") h->arena_reuse = value ? 1 : 0;
   else if (n == "clear_plans") drop_plans(h);
   else {
     h->err = "unknown option " + n;

@@ -154,6 +154,11 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes
  *                   resident, two accumulator sets in TMEM): halves the weight bytes pulled from L2 per item on the
  *                   layers that are L2->SM ingest bound; 0 = one item per weight pass
+ *   "plane_skip"  : 1 = lo planes that no consumer reads (destinations of single-pass convs) are neither gathered nor
+ *                   written (default), 0 = always both planes
+ *   "mma_straight": 1 = with resident weights one elected lane issues a whole activation stage as straight-line code
+ *                   (default), 0 = per-tap issue loop
+ *   "arena_reuse" : 1 = activation buffers are recycled inside a plan by liveness (default), 0 = one buffer per tensor
  *   "fuse_rgb_head": 1 = the linear 1x1 RGB head and the crop run in the epilogue of the decoder's last 3x3 conv (default;
  *                   the 64-channel activation is never stored), 0 = separate kernel
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)

@@ -23,7 +23,7 @@ ALL = (1 << nst) - 1
 variants = [{}, {"conv3x3_2cta": 0}, {"conv3x3_2cta": 2}, {"conv3x3_v2": 0}, {"conv3x3_halo": 0}, {"conv3x3_halo": 1},
             {"conv3x3_halo": 3}, {"conv3x3_halo": 3, "conv3x3_2cta": 2}, {"fe_conv0_tc": 1}, {"fuse_rgb_head": 0},
             {"fe_conv0_tc": 1, "fuse_rgb_head": 0, "conv3x3_halo": 2}, {"conv3x3_dual": 1},
-            {"conv3x3_dual": 1, "conv3x3_2cta": 2}]
+            {"conv3x3_dual": 1, "conv3x3_2cta": 2}, {"mma_straight": 0}, {"plane_skip": 0}, {"arena_reuse": 0}]
 bad = 0
 for var in variants:
     for mask in (0, dflt, ALL):
