@@ -740,9 +740,8 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.conv3x3_dual = (fe_conv0_tc & 4) ? 1 : 0;
   P.plane_skip = (fe_conv0_tc & 8) ? 0 : 1;
   P.mma_straight = (fe_conv0_tc & 16) ? 0 : 1;
-  if (fe_conv0_tc & 32) P.reuse = false;
   P.onepass_mask = onepass_mask;
-  P.reuse = !keep_debug && !use_lanes;
+  P.reuse = !keep_debug && !use_lanes && !(fe_conv0_tc & 32);
   P.h = h;
   P.w = w;
   P.conv_impl = conv_impl;
