@@ -146,8 +146,14 @@ def interpolate_recursively(engine: Engine, frame0: np.ndarray, frame1: np.ndarr
 # a slot of a gather buffer are passed without copies); the gloo tests use a CPU stand-in.
 
 def device_engine(interp):
-    """Adapts an `Interpolator` to the `engine_dev(x0, x1, out)` tensor-view interface."""
+    """Adapts an `Interpolator` to the `engine_dev(x0, x1, out)` tensor-view interface.
+
+    Stream semantics: the call is ordered after everything already enqueued on torch's CURRENT stream and everything
+    enqueued on the current stream afterwards (NCCL collectives, copies) is ordered after it. The engine runs on a
+    dedicated side stream joined to the current one with events, because torch's default stream is the NULL handle,
+    which `film_interpolate_device` reads as "use the engine's own stream"."""
     import torch
+    side = {}
 
     def run(x0, x1, out):
         h, w, c = x0.shape
@@ -155,9 +161,16 @@ def device_engine(interp):
             assert t.dtype == torch.float32 and t.is_cuda and t.shape == (h, w, 3)
             assert t.stride(2) == 1 and t.stride(1) == 3, "inner dims must be dense (row-pitched view)"
         assert x0.stride(0) == x1.stride(0), "x0 and x1 must share the row pitch"
+        dev = x0.device
+        if dev not in side:
+            side[dev] = torch.cuda.Stream(device=dev)
+        es, cur = side[dev], torch.cuda.current_stream(dev)
+        es.wait_stream(cur)
         interp.interpolate_device(x0.data_ptr(), x1.data_ptr(), 1, h, w, out.data_ptr(),
-                                  in_pitch=x0.stride(0), out_pitch=out.stride(0),
-                                  stream=torch.cuda.current_stream(x0.device).cuda_stream)
+                                  in_pitch=x0.stride(0), out_pitch=out.stride(0), stream=es.cuda_stream)
+        cur.wait_stream(es)
+        for t in (x0, x1, out):
+            t.record_stream(es)
     return run
 
 
