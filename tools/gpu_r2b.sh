@@ -2,10 +2,12 @@
 # round 2, GPU call B: full parity suite, kernel-option A/B benches on one box, precision study (2 seeds),
 # the complete bench line (with the 4K / 8K / 720p workloads), ncu evidence.
 mkdir -p gpurun_out
-T=r2b
+T=r2c
+bash tools/gpu_bisect.sh
+source gpurun_out/good_env.sh
+cat gpurun_out/good_env.sh
 timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
 tail -25 gpurun_out/${T}_pytest.log
-timeout 600 python tools/gpu_sanity.py > gpurun_out/${T}_sanity.log 2>&1; echo "sanity rc=$?"; grep -c "^OK" gpurun_out/${T}_sanity.log; grep -E "BAD|ERROR" gpurun_out/${T}_sanity.log | head
 for cfg in "default" "FILM_HALO=3" "FILM_2CTA=2" "FILM_2CTA=0" "FILM_FE0_TC=1" "FILM_RGB_FUSE=0" "FILM_DUAL=1" "FILM_STRAIGHT=0" "FILM_PLANE_SKIP=0"; do
   name=$(echo $cfg | tr '=' '_')
   if [ "$cfg" = "default" ]; then envs=""; else envs="$cfg"; fi
