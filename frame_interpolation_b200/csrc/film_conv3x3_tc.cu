@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             }
             __syncwarp();
             kb += kStageTaps;
-          } else
+          } else {
           for (int t = 0; t < kStageTaps; ++t, ++kb) {
             uint32_t sw;
             int ws = 0;
@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             __syncwarp();
             if (!resident) rw.advance(NW);
           }
+          }  // per-tap issue loop
           ra.advance(NA);
         }
       }

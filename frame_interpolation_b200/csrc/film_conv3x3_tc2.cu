@@ -230,7 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
-    } else
+    } else {
     for (int item = item0; item < nitems; item += item_step) {
       const int sp = item / n_nt, n0 = (item % n_nt) * BN;
       const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
@@ -289,6 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
       }
     }
+    }  // one item per weight pass
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ============================
     if (leader) {
@@ -373,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               }
               __syncwarp();
               kb += kStageTaps;
-            } else
+            } else {
             for (int t = 0; t < kStageTaps; ++t, ++kb) {
               uint32_t sw;
               int ws = 0;
@@ -440,6 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               __syncwarp();
               if (!resident) rw.advance(NW);
             }
+            }  // per-tap issue loop
             ra.advance(NA);
           }
         }
