@@ -2,7 +2,7 @@
 # Bisects the round-2 optimisations on the GPU: every configuration in its own process.
 # Leaves the maximal working environment in gpurun_out/good_env.sh (sourced by the follow-up steps).
 mkdir -p gpurun_out
-L=gpurun_out/r2c_bisect.log
+L=gpurun_out/${BISECT_TAG:-r2c}_bisect.log
 : > $L
 OFF="FILM_STRAIGHT=0 FILM_RGB_FUSE=0 FILM_FE0_TC=1 FILM_PLANE_SKIP=0 FILM_ARENA_REUSE=0"
 run() { tag=$1; shift; env "$@" timeout 300 python tools/gpu_quick.py $tag 2>&1 | grep -E "^QUICK" >> $L || echo "QUICK $tag FAIL (no output / timeout)" >> $L; tail -1 $L; }

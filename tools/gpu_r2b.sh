@@ -2,7 +2,8 @@
 # round 2, GPU call B: full parity suite, kernel-option A/B benches on one box, precision study (2 seeds),
 # the complete bench line (with the 4K / 8K / 720p workloads), ncu evidence.
 mkdir -p gpurun_out
-T=r2c
+T=${1:-r2c}
+export BISECT_TAG=$T
 bash tools/gpu_bisect.sh
 source gpurun_out/good_env.sh
 cat gpurun_out/good_env.sh
