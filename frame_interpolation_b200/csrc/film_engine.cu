@@ -1167,7 +1167,8 @@ struct film_handle {
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
   int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
-  int conv3x3_dual = 0;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass
+  int conv3x3_dual = 1;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass (default: -2.3 % step
+                          // time in the same-box A/B of profiles/r2d_variants_ab.md)
   int plane_skip = 1, mma_straight = 1, arena_reuse = 1;   // round-2 optimisations, individually switchable (A/B, bisecting)
   uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
   size_t u8_bytes = 0;

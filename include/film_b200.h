@@ -148,12 +148,13 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "conv3x3_halo": wide halo boxes -- one (64 ch, 10 px, 18 rows) TMA box per chunk serves all nine taps
  *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
  *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes,
- *                   3 = also the 32-channel-chunk layers (experimental: not yet validated on hardware)
+ *                   3 = also the 32-channel-chunk layers (validated on hardware in round 2: parity-clean, step time
+ *                       within noise of 2 -- profiles/r2d_variants_ab.md -- so 2 stays the default)
  *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image
  *                   (default), 1 = tensor-core kernel over a 32-channel-padded split image (comparison)
  *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes
  *                   resident, two accumulator sets in TMEM): halves the weight bytes pulled from L2 per item on the
- *                   layers that are L2->SM ingest bound; 0 = one item per weight pass
+ *                   layers that are L2->SM ingest bound (default); 0 = one item per weight pass
  *   "plane_skip"  : 1 = lo planes that no consumer reads (destinations of single-pass convs) are neither gathered nor
  *                   written (default), 0 = always both planes
  *   "mma_straight": 1 = with resident weights one elected lane issues a whole activation stage as straight-line code

@@ -293,7 +293,8 @@ def test_cli_end_to_end(tmp_path, synthetic_weights):
 
 @pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0),
                                           ("conv3x3_halo", 0), ("conv3x3_halo", 1), ("conv3x3_halo", 2), ("conv3x3_halo", 3),
-                                          ("fe_conv0_tc", 1), ("fuse_rgb_head", 0), ("conv3x3_dual", 1)])
+                                          ("fe_conv0_tc", 1), ("fuse_rgb_head", 0), ("conv3x3_dual", 0),
+                                          ("mma_straight", 0), ("plane_skip", 0), ("arena_reuse", 0)])
 def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers, wide-halo boxes off /
     pair-only; the default is wide halo in both persistent kernels) meets the same bar."""
@@ -305,7 +306,9 @@ def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     out = eng(x0, x1, DT)
     assert np.abs(out.astype(np.float64) - ref).max() < PLAN
     default = Interpolator(synthetic_weights[0], align=64)
-    assert np.abs(out - default(x0, x1, DT)).max() < 1e-4      # same precision plan, different kernels
+    # same precision plan, different kernels: accumulation-order differences of ~1e-6 flip fp16 roundings inside the
+    # single-pass stages, so two plan-mode results agree to the plan's own noise, not to 1e-6
+    assert np.abs(out - default(x0, x1, DT)).max() < 2.5e-4
     for e in (eng, default):
         e.set_option("onepass_mask", 0)
     out3 = eng(x0, x1, DT)

@@ -26,12 +26,15 @@ timeout 1200 python tools/precision_study.py --height 1080 --width 1920 --seeds 
 tail -3 gpurun_out/${T}_precision.log
 timeout 900 python bench.py --steps 20 --warmup 3 --op-table gpurun_out/${T}_ops.csv > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/${T}_bench.json; tail -5 gpurun_out/${T}_bench.err
-# ncu: launch list of one eager call (second call), light sections for every kernel, full set for the conv kernels and gathers
+# ncu: launch list of one eager call (second call); light sections for EVERY kernel of a call (DRAM bytes, L2->SM bytes, tensor
+# pipe, issue slots per launch); full set + source for the first launches of each tensor-core kernel and the gathers.
+# gpurun brings back at most 64 MiB: keep the reports small and drop the biggest ones if the total still exceeds it.
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python tools/profile_step.py 1 > gpurun_out/${T}_ncu_list.log 2>&1
 timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section SchedulerStats --clock-control none -s 140 -c 140 -f -o gpurun_out/${T}_all python tools/profile_step.py 1 > gpurun_out/${T}_ncu_all.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_tc2 -c 20 -f -o gpurun_out/${T}_pair python tools/profile_step.py 0 > gpurun_out/${T}_ncu_pair.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_conv3x3_tc<" -c 30 -f -o gpurun_out/${T}_single python tools/profile_step.py 0 > gpurun_out/${T}_ncu_single.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_flow_warp|k_fusion_warp|k_conv_tc" -c 24 -f -o gpurun_out/${T}_misc python tools/profile_step.py 0 > gpurun_out/${T}_ncu_misc.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_tc2 -c 4 -f -o gpurun_out/${T}_pair python tools/profile_step.py 0 > gpurun_out/${T}_ncu_pair.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_conv3x3_tc<" -c 4 -f -o gpurun_out/${T}_single python tools/profile_step.py 0 > gpurun_out/${T}_ncu_single.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_flow_warp|k_fusion_warp" -c 4 -f -o gpurun_out/${T}_gather python tools/profile_step.py 0 > gpurun_out/${T}_ncu_gather.log 2>&1
+while [ $(du -sm gpurun_out | cut -f1) -gt 58 ]; do big=$(ls -S gpurun_out/*.ncu-rep | head -1); echo "dropping $big"; rm -f $big; done
 # memcheck of one small network call (arena reuse, lo-plane skipping, fused epilogues): any out-of-bounds access shows up here
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/${T}_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a gpurun_out/${T}_memcheck.log
 tail -4 gpurun_out/${T}_memcheck.log
