@@ -25,5 +25,5 @@ echo "export $GOOD" > gpurun_out/good_env.sh
 [ -z "$GOOD" ] && echo "true" > gpurun_out/good_env.sh
 echo "good env: $GOOD" | tee -a $L
 env $GOOD QUICK_BIG=1 timeout 300 python tools/gpu_quick.py good_set 2>&1 | grep -E "^QUICK" | tee -a $L
-env $GOOD QUICK_BIG=1 FILM_DUAL=1 timeout 300 python tools/gpu_quick.py good_set_dual 2>&1 | grep -E "^QUICK" | tee -a $L
+env $GOOD QUICK_BIG=1 FILM_DUAL=0 timeout 300 python tools/gpu_quick.py good_set_nodual 2>&1 | grep -E "^QUICK" | tee -a $L
 env $GOOD QUICK_BIG=1 FILM_HALO=3 timeout 300 python tools/gpu_quick.py good_set_halo3 2>&1 | grep -E "^QUICK" | tee -a $L
