@@ -1162,8 +1162,9 @@ struct film_handle {
   int use_lanes = 0;   // stream lanes measured no gain at 1080p (smem-saturating kernels cannot co-reside)
   int conv3x3_v2 = 1;  // persistent tap-reuse kernel for 3x3 convs
   int conv3x3_2cta = 1;  // CTA-pair (cta_group::2) kernel for streamed-weight 3x3 convs on the large levels
-  int conv3x3_halo = 2;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
-                         // persistent kernels (default), 3 also the 32-channel-chunk layers (experimental)
+  int conv3x3_halo = 3;  // wide halo boxes (one 10-px box per chunk serves nine taps): 0 off, 1 pair kernel, 2 both
+                         // persistent kernels, 3 also the 32-channel-chunk layers (default: validated on hardware in
+                         // round 2, -0.6 % / -2.0 % step time in two same-box A/Bs, profiles/r2c|r2d_variants_ab.md)
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
   int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel

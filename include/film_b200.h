@@ -146,10 +146,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "conv3x3_2cta": 1 = CTA-pair (tcgen05 cta_group::2, M = 256) kernel for the streamed-weight 3x3
  *                   convs of the large pyramid levels (default), 0 = off, 2 = every eligible layer
  *   "conv3x3_halo": wide halo boxes -- one (64 ch, 10 px, 18 rows) TMA box per chunk serves all nine taps
- *                   (UMMA descriptors at pixel offsets): 2 = both persistent kernels (default),
- *                   1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes,
- *                   3 = also the 32-channel-chunk layers (validated on hardware in round 2: parity-clean, step time
- *                       within noise of 2 -- profiles/r2d_variants_ab.md -- so 2 stays the default)
+ *                   (UMMA descriptors at pixel offsets): 3 = both persistent kernels, 64- and 32-channel chunks
+ *                   (default: validated on hardware in round 2, -0.6 % / -2.0 % step time in two same-box A/Bs),
+ *                   2 = 64-channel chunks only, 1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
  *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image
  *                   (default), 1 = tensor-core kernel over a 32-channel-padded split image (comparison)
  *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes

@@ -26,4 +26,4 @@ echo "export $GOOD" > gpurun_out/good_env.sh
 echo "good env: $GOOD" | tee -a $L
 env $GOOD QUICK_BIG=1 timeout 300 python tools/gpu_quick.py good_set 2>&1 | grep -E "^QUICK" | tee -a $L
 env $GOOD QUICK_BIG=1 FILM_DUAL=0 timeout 300 python tools/gpu_quick.py good_set_nodual 2>&1 | grep -E "^QUICK" | tee -a $L
-env $GOOD QUICK_BIG=1 FILM_HALO=3 timeout 300 python tools/gpu_quick.py good_set_halo3 2>&1 | grep -E "^QUICK" | tee -a $L
+env $GOOD QUICK_BIG=1 FILM_HALO=2 timeout 300 python tools/gpu_quick.py good_set_halo2 2>&1 | grep -E "^QUICK" | tee -a $L
