@@ -177,67 +177,90 @@ __global__ void __launch_bounds__(256) k_conv0_c3(const float* __restrict__ img,
 // Exact fp32 arithmetic (the reference's own precision); writes the split planes of the 64-channel output.
 // ------------------------------------------------------------------------------------------
 constexpr int kC0H = 8, kC0W = 16;
+constexpr int kC0Tiles = 4;   // consecutive tiles along x per block: weights are staged once, the next tile's input patch is
+                              // fetched into registers while the current one is computed (the block prologue -- 7 KB of
+                              // weights + a global round trip for the patch -- cost as much as the 1,728 FMAs of one tile)
+constexpr int kC0Patch = (kC0H + 2) * (kC0W + 2) * 3;           // 540 floats
+constexpr int kC0PatchRegs = (kC0Patch + 127) / 128;            // 5 per thread
+__device__ __forceinline__ float fe_patch_load(const float* __restrict__ img, int b, int H, int W, int y0, int x0, int i) {
+  const int c = i % 3, px = (i / 3) % (kC0W + 2), py = i / (3 * (kC0W + 2));
+  const int yy = y0 + py - 1, xx = x0 + px - 1;
+  return (i < kC0Patch && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (((int64_t)b * H + yy) * W + xx) * 3 + c) : 0.f;
+}
 __global__ void __launch_bounds__(128) k_fe_conv0(const float* __restrict__ img, int H, int W,
                                                   const float* __restrict__ w, const float* __restrict__ bias,
                                                   sp_t* __restrict__ out_hi, sp_t* __restrict__ out_lo, int lo_skip) {
   __shared__ float4 ws[27 * 16];                            // [tap * 3 + ci][64 channels]
   __shared__ float bs[64];
-  __shared__ float patch[(kC0H + 2) * (kC0W + 2) * 3];      // zero outside the image == SAME padding
+  __shared__ float patch[kC0Patch];                         // zero outside the image == SAME padding
   const int tid = threadIdx.x;
-  const int b = blockIdx.z, y0 = blockIdx.y * kC0H, x0 = blockIdx.x * kC0W;
+  const int b = blockIdx.z, y0 = blockIdx.y * kC0H, xb = blockIdx.x * (kC0W * kC0Tiles);
   for (int i = tid; i < 27 * 16; i += 128) ws[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   if (tid < 64) bs[tid] = bias[tid];
-  for (int i = tid; i < (kC0H + 2) * (kC0W + 2) * 3; i += 128) {
-    const int c = i % 3, px = (i / 3) % (kC0W + 2), py = i / (3 * (kC0W + 2));
-    const int yy = y0 + py - 1, xx = x0 + px - 1;
-    patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (((int64_t)b * H + yy) * W + xx) * 3 + c) : 0.f;
-  }
-  __syncthreads();
+  float nxt[kC0PatchRegs];
+#pragma unroll
+  for (int j = 0; j < kC0PatchRegs; ++j) nxt[j] = fe_patch_load(img, b, H, W, y0, xb, tid + 128 * j);
   const int warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, cx = (lane & 3) * 4;
-  float acc[4][16];
+  const int y = y0 + r;
+#pragma unroll 1
+  for (int tile = 0; tile < kC0Tiles; ++tile) {
+    const int x0 = xb + tile * kC0W;
+    if (x0 >= W) break;                                     // block-uniform
+    __syncthreads();                                        // everyone finished reading the previous patch
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+    for (int j = 0; j < kC0PatchRegs; ++j)
+      if (tid + 128 * j < kC0Patch) patch[tid + 128 * j] = nxt[j];
+    __syncthreads();
+    if (tile + 1 < kC0Tiles && x0 + kC0W < W) {             // prefetch the next tile's patch (latency hidden by the FMAs)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+      for (int j = 0; j < kC0PatchRegs; ++j) nxt[j] = fe_patch_load(img, b, H, W, y0, x0 + kC0W, tid + 128 * j);
+    }
+    float acc[4][16];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    float in[18];                                           // 6 pixels x 3 channels of input row r + ky
-    const float* pr = patch + ((r + ky) * (kC0W + 2) + cx) * 3;
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int j = 0; j < 18; ++j) in[j] = pr[j];
+      for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
+    for (int ky = 0; ky < 3; ++ky) {
+      float in[18];                                         // 6 pixels x 3 channels of input row r + ky
+      const float* pr = patch + ((r + ky) * (kC0W + 2) + cx) * 3;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float4* wk = ws + ((ky * 3 + kx) * 3 + ci) * 16 + warp * 4;
-        const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2], w3 = wk[3];
-        const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+      for (int j = 0; j < 18; ++j) in[j] = pr[j];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float v = in[(p + kx) * 3 + ci];
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v, wv[j], acc[p][j]);
+        for (int ci = 0; ci < 3; ++ci) {
+          const float4* wk = ws + ((ky * 3 + kx) * 3 + ci) * 16 + warp * 4;
+          const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2], w3 = wk[3];
+          const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = in[(p + kx) * 3 + ci];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v, wv[j], acc[p][j]);
+          }
+        }
+    }
+    if (y < H) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int x = x0 + cx + p;
+        if (x < W) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = leaky(acc[p][j] + bs[warp * 16 + j]);
+          const int64_t o = (((int64_t)b * H + y) * W + x) * 64 + warp * 16;
+          if (lo_skip) pack_store16_hi(f, out_hi + o);
+          else pack_store16(f, out_hi + o, out_lo + o);
         }
       }
-  }
-  const int y = y0 + r;
-  if (y >= H) return;
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int x = x0 + cx + p;
-    if (x >= W) break;
-    float f[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = leaky(acc[p][j] + bs[warp * 16 + j]);
-    const int64_t o = (((int64_t)b * H + y) * W + x) * 64 + warp * 16;
-    if (lo_skip) pack_store16_hi(f, out_hi + o);
-    else pack_store16(f, out_hi + o, out_lo + o);
+    }
   }
 }
 cudaError_t launch_fe_conv0(const float* img, int B, int H, int W, const float* w, const float* bias, sp_t* out_hi,
                             sp_t* out_lo, bool lo_skip, cudaStream_t st) {
-  dim3 grid((W + kC0W - 1) / kC0W, (H + kC0H - 1) / kC0H, B);
+  dim3 grid((W + kC0W * kC0Tiles - 1) / (kC0W * kC0Tiles), (H + kC0H - 1) / kC0H, B);
   k_fe_conv0<<<grid, 128, 0, st>>>(img, H, W, w, bias, out_hi, out_lo, lo_skip ? 1 : 0);
   return cudaGetLastError();
 }
