@@ -68,7 +68,13 @@ struct alignas(64) ConvProblem {
   // kernel only): this conv is the decoder's last 3x3 (64 -> 64, LeakyReLU); the epilogue applies the linear 1x1
   // 64 -> 3 output conv on the fp32 activations and writes the cropped fp32 image -- the 64-channel tensor is never
   // stored.  head_w4 = [64][3], head_b4 = [3], head_v = image [crop_h][crop_w][3] with row pitch crop_pitch floats.
+  // epilogue mode 3 ("flow head in the last 3x3", persistent single-CTA kernel, Cout <= 64): this conv is conv_2 of a
+  // FlowEstimator (pyramid_flow_estimator.py:66-72); the epilogue applies conv_3 (1x1, nf -> nf/2, LeakyReLU, head_w3 =
+  // [nf][nf/2], head_b3), conv_4 (1x1 -> 2, linear, head_w4 / head_b4) and the residual add `v = r + v_up` (:161) on the
+  // fp32 activations: the nf-channel tensor is never stored and the separate head launch disappears.
   int epi_mode;
+  const float* head_w3;
+  const float* head_b3;
   int crop_y, crop_x, crop_h, crop_w;
   int64_t crop_pitch;
   const float* head_w4;   // [cout][2]

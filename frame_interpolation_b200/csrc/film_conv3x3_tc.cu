@@ -57,6 +57,9 @@ constexpr int kMaxRing = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (4 * kMaxRing + 4);
 constexpr int kFixedBytes = kBarBytes + 16 + 512 * 4 /*bias*/ + 64 /*src table: 16 ints*/ + 1024 /*align*/ + 64;
+// flow-head epilogue (epi_mode 3): partial sums [32 hidden][128 rows] + W3 [64][32] + b3 / W4 / b4, after the src table
+constexpr int kHeadPart = 32 * 128 * 4, kHeadW3 = 64 * 32 * 4, kHeadMisc = 512;
+constexpr int kHeadBytes = kHeadPart + kHeadW3 + kHeadMisc;
 
 __host__ __device__ inline int w_tap_bytes(int bn, int kc, int planes = 2) { return bn * kc * 2 * planes; }  // [BN x KC] hi (+ lo)
 
@@ -388,6 +391,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     const int crop_y = prob->crop_y, crop_x = prob->crop_x, crop_h = prob->crop_h, crop_w = prob->crop_w;
     const int64_t crop_pitch = prob->crop_pitch;
     float* const part = bias_smem + 64;   // [128 rows][3] (bias_smem holds 64 biases in this mode, 512 floats in all)
+    // flow-head mode (BN <= 64): hidden units = BN / 2; each warp of a lane quarter accumulates the partial sums of its
+    // channels for every hidden unit, the pair combines through smem ([hidden][row]: conflict-free) and finishes the head
+    const bool fhead = prob->epi_mode == 3;
+    constexpr int kHid = BN <= 64 ? BN / 2 : 1;
+    float* const hpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(src_tab) + 64);   // [kHid][128]
+    float* const w3s = hpart + kHeadPart / 4;                                                   // [BN][kHid]
+    float* const hmisc = w3s + kHeadW3 / 4;                                                     // b3[kHid] | w4[kHid][2] | b4[2]
+    if (fhead) {
+      if constexpr (BN <= 64) {
+        for (int i = threadIdx.x - 64; i < BN * kHid; i += 32 * kEpiWarps) w3s[i] = prob->head_w3[i];
+        for (int i = threadIdx.x - 64; i < kHid; i += 32 * kEpiWarps) hmisc[i] = prob->head_b3[i];
+        for (int i = threadIdx.x - 64; i < 2 * kHid; i += 32 * kEpiWarps) hmisc[kHid + i] = prob->head_w4[i];
+        if (threadIdx.x - 64 < 2) hmisc[3 * kHid + threadIdx.x - 64] = prob->head_b4[threadIdx.x - 64];
+      }
+      asm volatile("bar.sync 5, %0;" ::"r"(32 * kEpiWarps) : "memory");   // epilogue warps only
+    }
+    const float* const head_vup = prob->head_vup;
+    float* const head_res = prob->head_res;
+    float* const head_vout = prob->head_v;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
@@ -402,6 +424,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      [[maybe_unused]] float hp[kHid];
+      if constexpr (BN <= 64) {
+#pragma unroll
+        for (int hh = 0; hh < kHid; ++hh) hp[hh] = 0.f;
+      }
 #pragma unroll 1
       for (int cc = half; cc < BN / 16; cc += 2) {
         if (n0 + cc * 16 >= cout) break;
@@ -423,7 +450,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
             float x = __uint_as_float(v[j]) + bias_smem[n0 + cc * 16 + j];
             f[j] = act ? leaky(x) : x;
           }
-          if (rgb) {
+          if (fhead) {
+            if constexpr (BN <= 64) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4* wr = reinterpret_cast<const float4*>(w3s + (cc * 16 + j) * kHid);   // broadcast reads
+#pragma unroll
+                for (int h4 = 0; h4 < kHid / 4; ++h4) {
+                  const float4 wv = wr[h4];
+                  hp[4 * h4] = fmaf(f[j], wv.x, hp[4 * h4]);
+                  hp[4 * h4 + 1] = fmaf(f[j], wv.y, hp[4 * h4 + 1]);
+                  hp[4 * h4 + 2] = fmaf(f[j], wv.z, hp[4 * h4 + 2]);
+                  hp[4 * h4 + 3] = fmaf(f[j], wv.w, hp[4 * h4 + 3]);
+                }
+              }
+            }
+          } else if (rgb) {
             const float* hw = head_w + (n0 + cc * 16) * 3;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -454,7 +496,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tail + 8u * (4 * kMaxRing + 2 + acc));
-      if (rgb) {
+      if (fhead) {
+        if constexpr (BN <= 64) {
+          if (half == 1) {
+#pragma unroll
+            for (int hh = 0; hh < kHid; ++hh) hpart[hh * 128 + r] = hp[hh];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (half == 0 && valid) {
+            float f0 = hmisc[3 * kHid], f1 = hmisc[3 * kHid + 1];
+#pragma unroll
+            for (int hh = 0; hh < kHid; ++hh) {
+              const float x = leaky(hp[hh] + hpart[hh * 128 + r] + hmisc[hh]);     // conv_3: bias + LeakyReLU
+              f0 = fmaf(x, hmisc[kHid + 2 * hh], f0);                                  // conv_4: linear
+              f1 = fmaf(x, hmisc[kHid + 2 * hh + 1], f1);
+            }
+            float2 res = make_float2(f0, f1), tot = res;
+            if (head_vup) {
+              const float2 u = reinterpret_cast<const float2*>(head_vup)[opix];
+              tot.x += u.x;
+              tot.y += u.y;
+            }
+            reinterpret_cast<float2*>(head_res)[opix] = res;
+            reinterpret_cast<float2*>(head_vout)[opix] = tot;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // hpart[] is rewritten by the next tile
+        }
+      } else if (rgb) {
         if (half == 1) {
           part[r * 3] = r0;
           part[r * 3 + 1] = r1;
@@ -486,7 +554,8 @@ int smem_bytes_for(const ConvProblem& h, int bn) {
   const int nkb = h.ktot / h.kchunk;
   const int planes = h.passes == 1 ? 1 : 2;
   const int w = h.v2_resident ? nkb * w_tap_bytes(bn, h.kchunk, planes) : h.v2_nw * w_tap_bytes(bn, h.kchunk, planes);
-  return h.v2_na * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo, planes) + w + kFixedBytes;
+  return h.v2_na * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo, planes) + w + kFixedBytes +
+         (h.epi_mode == 3 ? kHeadBytes : 0);
 }
 
 }  // namespace
@@ -520,22 +589,23 @@ void conv3x3_tc_plan(ConvProblem& h, int num_sms) {
   const int wtap = w_tap_bytes(bn, h.kchunk, planes);
   const int w_all = nkb * wtap;
   const bool can_resident = h.cout <= bn;
+  const int kLimit = kSmemLimit - (h.epi_mode == 3 ? kHeadBytes : 0);   // flow-head epilogue scratch
   // wide halo (the engine allows it per chunk size): 16x8 tiles only; resident weights win when both do not fit
   if (h.halo && (h.tile_h != 16 || h.tile_w != 8 ||
-                 (can_resident && w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 0, planes) + kFixedBytes <= kSmemLimit &&
-                  w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 1, planes) + kFixedBytes > kSmemLimit)))
+                 (can_resident && w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 0, planes) + kFixedBytes <= kLimit &&
+                  w_all + 2 * a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, 1, planes) + kFixedBytes > kLimit)))
     h.halo = 0;
   const int kAStage = a_stage_bytes_h(h.kchunk, h.tile_h, h.tile_w, h.halo, planes);
   h.v2_resident = 0;
-  if (can_resident && w_all + 2 * kAStage + kFixedBytes <= kSmemLimit) {
+  if (can_resident && w_all + 2 * kAStage + kFixedBytes <= kLimit) {
     h.v2_resident = 1;
-    int na = (kSmemLimit - kFixedBytes - w_all) / kAStage;
+    int na = (kLimit - kFixedBytes - w_all) / kAStage;
     const int na_max = h.halo ? 3 : 6;
     h.v2_na = na > na_max ? na_max : na;
     h.v2_nw = 1;
   } else {
     h.v2_na = h.halo ? 2 : (bn >= 128 ? 2 : 3);
-    int nw = (kSmemLimit - kFixedBytes - h.v2_na * kAStage) / wtap;
+    int nw = (kLimit - kFixedBytes - h.v2_na * kAStage) / wtap;
     h.v2_nw = nw > kMaxRing ? kMaxRing : nw;
   }
   const int ntiles = h.B * h.tiles_y * h.tiles_x * ((h.cout + bn - 1) / bn);

@@ -468,6 +468,7 @@ struct Plan {
   int fe_conv0_tc = 0;        // 1: cfeat_conv_0 on the tensor cores (32-channel-padded image), 0: fp32 FMA kernel
   int fuse_rgb_head = 1;      // RGB head + crop in the epilogue of the decoder's last conv
   int conv3x3_dual = 0;       // CTA-pair kernel: two spatial items per streamed weight pass
+  int fuse_flow_head = 1;     // flow head (conv_3, conv_4, residual add) in conv_2's epilogue on levels 0 and 1
   int plane_skip = 1;         // lo planes that no consumer reads are neither gathered nor written
   int mma_straight = 1;       // straight-line MMA issue for resident weights
   std::vector<void*> allocs;
@@ -597,12 +598,12 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
   // 3x3 SAME convs with a unit-stride destination run on the persistent tap-reuse kernel
   const int kc = pc.kchunk;
   cp.kchunk = kc;
-  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && (out || epi_mode == 2) && sy == 1 && sx == 1 &&
+  const bool v2 = P.conv3x3_v2 && P.conv_impl == 0 && pc.ntaps == 9 && (out || epi_mode >= 2) && sy == 1 && sx == 1 &&
                   (kc == kChunk || pc.cout <= 64);
   cp.epi_mode = epi_mode;
   int box_h, box_w;
   // CTA-pair kernel: large levels only (it needs 16x8 tiles and enough tile pairs to fill the SM pairs)
-  const bool want_pair = v2 && P.conv3x3_2cta && epi_mode != 2 &&   // (the RGB-head epilogue lives in the single-CTA kernel)
+  const bool want_pair = v2 && P.conv3x3_2cta && epi_mode < 2 &&   // (the RGB / flow-head epilogues live in the single-CTA kernel)
                          (P.conv3x3_2cta >= 2 ||  // >= 2: every eligible layer (testing)
                           (long)cp.B * ((cp.H + 15) / 16) * ((cp.W + 7) / 8) >= 4L * P.num_sms);
   if (v2) {
@@ -739,6 +740,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.fuse_rgb_head = (fe_conv0_tc & 2) ? 0 : 1;
   P.conv3x3_dual = (fe_conv0_tc & 4) ? 1 : 0;
   P.plane_skip = (fe_conv0_tc & 8) ? 0 : 1;
+  P.fuse_flow_head = (fe_conv0_tc & 64) ? 0 : 1;
   P.mma_straight = (fe_conv0_tc & 16) ? 0 : 1;
   P.onepass_mask = onepass_mask;
   P.reuse = !keep_debug && !use_lanes && !(fe_conv0_tc & 32);
@@ -939,8 +941,25 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     flow_src[1].bswap = second ? 0 : 1;
     add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], flow_src, 1, c0, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
-    add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l, ST_NONE);
-    if (P.conv_impl == 1) {
+    // levels whose predictor has <= 64 filters (0 and 1): conv_3, conv_4 and the residual add run in conv_2's epilogue
+    const bool fuse_head = P.conv_impl == 0 && P.conv3x3_v2 && P.fuse_flow_head && nf <= 64;
+    if (fuse_head) {
+      const size_t ci = add_conv(P, "flow_conv2+head" + lt, 9.0 * nf * nf + 1.0 * nf * (nf / 2) + (nf / 2) * 2.0, M.flow[p][2],
+                                 {{c1, 0}}, 1, nullptr, 0, ST_FLOW_L0 + l, ST_NONE, 1, 1, 0, 0, nullptr, false, 3);
+      ConvProblem& hp = P.h_probs[ci];
+      if (hp.bn != nf || hp.pair) throw Error{FILM_ERR_UNSUPPORTED, "flow-head epilogue expects one N tile on the single-CTA kernel"};
+      hp.head_w3 = M.flow_w3[p];
+      hp.head_b3 = M.flow_b3[p];
+      hp.head_w4 = M.flow_w4[p];
+      hp.head_b4 = M.flow_b4[p];
+      hp.head_vup = vup;
+      hp.head_res = res[l];
+      hp.head_v = v[l];
+    } else {
+      add_conv(P, "flow_conv2" + lt, 9.0 * nf * nf, M.flow[p][2], {{c1, 0}}, 1, c2, 0, ST_FLOW_L0 + l, ST_NONE);
+    }
+    if (fuse_head) {
+    } else if (P.conv_impl == 1) {
       // CUDA-core validation path keeps the standalone fp32 head kernel
       const float *w3 = M.flow_w3[p], *b3 = M.flow_b3[p], *w4 = M.flow_w4[p], *b4 = M.flow_b4[p];
       float *rr = res[l], *vv = v[l];
@@ -1171,6 +1190,7 @@ struct film_handle {
   int conv3x3_dual = 1;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass (default: -2.3 % step
                           // time in the same-box A/B of profiles/r2d_variants_ab.md)
   int plane_skip = 1, mma_straight = 1, arena_reuse = 1;   // round-2 optimisations, individually switchable (A/B, bisecting)
+  int fuse_flow_head = 1;
   uint8_t* u8_stage = nullptr;  // film_interpolate_u8: [x0][x1][out] on the device
   size_t u8_bytes = 0;
   int num_sms = 148;
@@ -1240,7 +1260,7 @@ static void drop_plans(film_handle* h) {
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 64 + h->arena_reuse * 32 + h->mma_straight * 16 + h->plane_skip * 8 + h->conv3x3_dual * 4 +
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 128 + h->fuse_flow_head * 64 + h->arena_reuse * 32 + h->mma_straight * 16 + h->plane_skip * 8 + h->conv3x3_dual * 4 +
                h->fuse_rgb_head * 2 + h->fe_conv0_tc);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
@@ -1248,7 +1268,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
                    h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
-                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32));
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64));
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1257,7 +1277,7 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
                    h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
-                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32));
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64));
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1346,6 +1366,7 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     if (const char* e6 = getenv("FILM_RGB_FUSE")) h->fuse_rgb_head = atoi(e6) ? 1 : 0;
     if (const char* e7 = getenv("FILM_DUAL")) h->conv3x3_dual = atoi(e7) ? 1 : 0;
     if (const char* e8 = getenv("FILM_PLANE_SKIP")) h->plane_skip = atoi(e8) ? 1 : 0;
+    if (const char* e11 = getenv("FILM_FLOW_HEAD_FUSE")) h->fuse_flow_head = atoi(e11) ? 1 : 0;
     if (const char* e9 = getenv("FILM_STRAIGHT")) h->mma_straight = atoi(e9) ? 1 : 0;
     if (const char* e10 = getenv("FILM_ARENA_REUSE")) h->arena_reuse = atoi(e10) ? 1 : 0;
     if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
@@ -1415,6 +1436,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "fuse_rgb_head") h->fuse_rgb_head = value ? 1 : 0;
   else if (n == "conv3x3_dual") h->conv3x3_dual = value ? 1 : 0;
   else if (n == "plane_skip") h->plane_skip = value ? 1 : 0;
+  else if (n == "fuse_flow_head") h->fuse_flow_head = value ? 1 : 0;
   else if (n == "mma_straight") h->mma_straight = value ? 1 : 0;
   else if (n == "arena_reuse") h->arena_reuse = value ? 1 : 0;
   else if (n == "clear_plans") drop_plans(h);

@@ -159,6 +159,8 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "mma_straight": 1 = with resident weights one elected lane issues a whole activation stage as straight-line code
  *                   (default), 0 = per-tap issue loop
  *   "arena_reuse" : 1 = activation buffers are recycled inside a plan by liveness (default), 0 = one buffer per tensor
+ *   "fuse_flow_head": 1 = on the flow levels whose predictor has <= 64 filters (levels 0 and 1) conv_3, conv_4 and the
+ *                   residual add run in the epilogue of conv_2 (default), 0 = separate head launch
  *   "fuse_rgb_head": 1 = the linear 1x1 RGB head and the crop run in the epilogue of the decoder's last 3x3 conv (default;
  *                   the 64-channel activation is never stored), 0 = separate kernel
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)
