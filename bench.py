@@ -428,6 +428,28 @@ def main():
     # parity guard: device path and host path must agree bit for bit
     same = bool(np.array_equal(res, dout.cpu().numpy()))
 
+    # ---- the same call with 8-bit frames at the boundary (eval/util.py read_image / write_image semantics on the
+    #      device): a quarter of the PCIe bytes; reported next to `e2e`, never instead of it
+    e2e_u8 = None
+    try:
+        from frame_interpolation_b200 import eval_util
+        u0 = torch.from_numpy(eval_util.to_uint8(x0)).pin_memory().numpy()
+        u1 = torch.from_numpy(eval_util.to_uint8(x1)).pin_memory().numpy()
+        for _ in range(2):
+            eng.interpolate_u8(u0, u1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.interpolate_u8(u0, u1)
+        torch.cuda.synchronize()
+        t_u8 = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_u8, op=dist.ReduceOp.MAX)
+        e2e_u8 = {"value": world * K / float(t_u8.item()), "unit": "frames/s", "api": "Interpolator.interpolate_u8(x0, x1)",
+                  "h2d_bytes_per_step": 2 * int(u0.nbytes), "d2h_bytes_per_step": int(u0.nbytes)}
+    except Exception as exc:           # secondary number: never fatal
+        e2e_u8 = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- per-kernel pass (eager, one event pair per launch) -------------------------
     eng.set_option("time_ops", 1)
     acc = None
@@ -505,6 +527,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
                 "d2h_bytes_per_step": frame_bytes, "host_memory": "pinned", "api": "Interpolator.__call__(x0, x1, dt)",
                 "device_vs_host_path_bitwise_equal": same},
+        "e2e_u8": e2e_u8,
         "gpu_launches": int(prof["kernel_launches"]) * K,
         "clocks": sampler.summary(),
         "roofline": roofline,
