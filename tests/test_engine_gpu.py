@@ -218,7 +218,7 @@ def test_profile_and_op_table(engine):
     x0, x1 = synthetic.frame_pair(128, 128, seed=1, n_waves=4)
     engine(x0, x1, DT)
     p = engine.profile()
-    assert p["padded_h"] == 128 and p["kernel_launches"] > 100 and p["used_graph"] == 1
+    assert p["padded_h"] == 128 and p["kernel_launches"] > 90 and p["used_graph"] == 1
     assert abs(p["conv_flops"] - 2 * spec.conv_macs(128, 128)["total"]) / p["conv_flops"] < 1e-9
     tab = engine.op_table()
     assert sum(1 for r in tab if r["category"] == 0) > 60
