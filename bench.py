@@ -123,6 +123,9 @@ class ClockSampler:
 
 _BEST_THREADS = None
 REF_WALL_BUDGET_S = 200.0      # the reference arm must end "within a few minutes"
+# DRAM bytes (read + write) of the tensor-core conv launches of ONE 1080p call, summed from the committed ncu capture
+# profiles/r2e_ncu_counters_1080p.csv (tools/gpu_r2b.sh: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,...`)
+NCU_CONV_DRAM_BYTES_PER_STEP = 19.968e9
 
 
 def _pick_threads():
@@ -482,9 +485,12 @@ def main():
     roofline = {
         "bound": "tensor", "kernel": "k_conv_tc<BN> (tcgen05 implicit-GEMM conv, all call sites)",
         "achieved": ach_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": ach_tf / peaks["bf16_tflops_sustained"], "traffic": None,
-        "traffic_note": "roofline is over 84 launches of 3 kernels; ncu --set full on 22 of them "
-                        "(profiles/r1s_ncu_final.md): dram read+write == algorithmic bytes on every capture",
+        "frac": ach_tf / peaks["bf16_tflops_sustained"], "traffic": NCU_CONV_DRAM_BYTES_PER_STEP,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 75 tensor-core conv launches of one 1080p "
+                        "call, ncu capture of build r2e (profiles/r2e_ncu_counters_1080p.csv; dominant launch fusion_conv1@L1: "
+                        "1.55 GB in 1.24 ms, tensor pipe 79 %); `algorithmic_bytes_per_step` is the engine's own count (every "
+                        "source plane a call site consumes read once, every destination plane written once)",
+        "algorithmic_bytes_per_step": sum(a["alg_bytes"] for a in conv),
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
         "mma_kind": "tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate); per-stage precision plan: 1 pass (hi*hi) on "
                     + ",".join(one_pass) + "; 3 passes (hi*hi + hi*lo + lo*hi) on " + ",".join(three_pass) + " and the heads",

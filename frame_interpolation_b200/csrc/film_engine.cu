@@ -468,7 +468,7 @@ struct Plan {
   int fe_conv0_tc = 0;        // 1: cfeat_conv_0 on the tensor cores (32-channel-padded image), 0: fp32 FMA kernel
   int fuse_rgb_head = 1;      // RGB head + crop in the epilogue of the decoder's last conv
   int conv3x3_dual = 0;       // CTA-pair kernel: two spatial items per streamed weight pass
-  int fuse_flow_head = 1;     // flow head (conv_3, conv_4, residual add) in conv_2's epilogue on levels 0 and 1
+  int fuse_flow_head = 1;     // flow head (conv_3, conv_4, residual add) in conv_2 epilogue: 1 = level 0, 2 = levels 0 and 1
   int plane_skip = 1;         // lo planes that no consumer reads are neither gathered nor written
   int mma_straight = 1;       // straight-line MMA issue for resident weights
   std::vector<void*> allocs;
@@ -504,7 +504,7 @@ struct Plan {
   float* xin = nullptr;   // [2][h][w][3] unpadded inputs
   float* xout = nullptr;  // [h][w][3]
   cudaGraphExec_t graph = nullptr;
-  double conv_flops = 0, mma_flops = 0, warp_bytes = 0;
+  double conv_flops = 0, mma_flops = 0, warp_bytes = 0, last_conv_bytes = 0;
 
   // Activation arena with liveness-based reuse.  The schedule is built in execution order and replayed on ONE
   // stream (or as the graph captured from it), so a buffer released at build position i may back any buffer
@@ -719,6 +719,18 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     k_issued += (double)pc.src_chunks[si] * pc.ntaps * ((v2 || pair) ? pc.src_ksteps[si] * 16 : pc.kchunk);
   P.mma_flops += (double)cp.passes * 2.0 * (double)cp.B * cp.tiles_y * cp.tiles_x * kTileM * k_issued *
                  (double)(((pc.cout + bn - 1) / bn) * bn);
+  // algorithmic HBM bytes of this call site: every source plane it consumes read once, every destination plane written once
+  double alg_bytes = 0;
+  {
+    const double px = (double)cp.B * cp.H * cp.W, planes_in = cp.passes == 1 ? 1.0 : 2.0;
+    for (size_t si = 0; si < pc.src_chunks.size(); ++si) alg_bytes += px * pc.src_chunks[si] * pc.kchunk * 2.0 * planes_in;
+    if (out) alg_bytes += px * pc.cout * 2.0 * (cp.out_lo_skip ? 1.0 : 2.0);
+    if (pool_out) alg_bytes += px / 4.0 * pc.cout * 4.0;
+    if (epi_mode == 2) alg_bytes += px * 12.0;
+    if (!out && epi_mode != 2) alg_bytes += px * 24.0;   // flow heads: v_up read, residual and flow written
+    alg_bytes += (double)pc.cout * pc.ktot * 2.0 * planes_in;
+  }
+  P.last_conv_bytes = alg_bytes;
   if (no_op) return idx;  // the caller launches this problem as part of a group
   Plan* pp = &P;
   const int impl = P.conv_impl;
@@ -727,7 +739,7 @@ static size_t add_conv(Plan& P, const std::string& tag, double ref_macs_per_px, 
     if (pair) return launch_conv3x3_tc2(pp->d_probs + idx, pp->h_probs[idx], st);
     return v2 ? launch_conv3x3_tc(pp->d_probs + idx, pp->h_probs[idx], st)
               : launch_conv_tc(pp->d_probs + idx, pp->h_probs[idx], st);
-  }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W);
+  }, 2.0 * ref_macs_per_px * (double)cp.B * cp.H * cp.W, alg_bytes);
   return idx;
 }
 
@@ -740,7 +752,7 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
   P.fuse_rgb_head = (fe_conv0_tc & 2) ? 0 : 1;
   P.conv3x3_dual = (fe_conv0_tc & 4) ? 1 : 0;
   P.plane_skip = (fe_conv0_tc & 8) ? 0 : 1;
-  P.fuse_flow_head = (fe_conv0_tc & 64) ? 0 : 1;
+  P.fuse_flow_head = (fe_conv0_tc & 64) ? 0 : ((fe_conv0_tc & 128) ? 2 : 1);
   P.mma_straight = (fe_conv0_tc & 16) ? 0 : 1;
   P.onepass_mask = onepass_mask;
   P.reuse = !keep_debug && !use_lanes && !(fe_conv0_tc & 32);
@@ -941,8 +953,10 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
     flow_src[1].bswap = second ? 0 : 1;
     add_conv(P, "flow_conv0" + lt, 9.0 * 2 * C * nf, M.flow[p][0], flow_src, 1, c0, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
     add_conv(P, "flow_conv1" + lt, 9.0 * nf * nf, M.flow[p][1], {{c0, 0}}, 1, c1, 0, ST_FLOW_L0 + l, ST_FLOW_L0 + l);
-    // levels whose predictor has <= 64 filters (0 and 1): conv_3, conv_4 and the residual add run in conv_2's epilogue
-    const bool fuse_head = P.conv_impl == 0 && P.conv3x3_v2 && P.fuse_flow_head && nf <= 64;
+    // level 0 (32-filter predictor): conv_3, conv_4 and the residual add run in conv_2's epilogue.  The kernel supports
+    // nf <= 64, but per-op timing (profiles/r2e) shows the 64-filter level 1 epilogue-bound (32 x 32 FMAs per thread):
+    // 0.253 ms fused vs 0.224 ms as two launches, while level 0 gains (0.502 vs 0.566 ms) -- so only level 0 is fused.
+    const bool fuse_head = P.conv_impl == 0 && P.conv3x3_v2 && P.fuse_flow_head && nf <= (P.fuse_flow_head >= 2 ? 64 : 32);
     if (fuse_head) {
       const size_t ci = add_conv(P, "flow_conv2+head" + lt, 9.0 * nf * nf + 1.0 * nf * (nf / 2) + (nf / 2) * 2.0, M.flow[p][2],
                                  {{c1, 0}}, 1, nullptr, 0, ST_FLOW_L0 + l, ST_NONE, 1, 1, 0, 0, nullptr, false, 3);
@@ -1054,11 +1068,12 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
           if (py == 0 && px == 0) first = ci;
         }
       P.h_probs[first].group = 4;
+      const double up_bytes = 4.0 * P.last_conv_bytes;   // four parity classes, each reads the coarse sources once
       Plan* pq = &P;
       const double fl = 2.0 * 16.0 * M.fus_up[i][0].cin_ref * nf * (double)Hs[i + 1] * Ws[i + 1];
       P.add_op(0, "fusion_up@L" + std::to_string(i), [pq, first](cudaStream_t st) {
         return launch_conv_tc(pq->d_probs + first, pq->h_probs[first], st);
-      }, fl);
+      }, fl, up_bytes);
     } else {
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px)
@@ -1185,7 +1200,8 @@ struct film_handle {
                          // persistent kernels, 3 also the 32-channel-chunk layers (default: validated on hardware in
                          // round 2, -0.6 % / -2.0 % step time in two same-box A/Bs, profiles/r2c|r2d_variants_ab.md)
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
-  int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel (default), 1 = tensor-core kernel
+  int fe_conv0_tc = 1;  // cfeat_conv_0: 1 = tensor-core kernel over the 32-channel-padded image (default: 0.78 ms over
+                        // the 7 levels against 0.87 ms, per-op timing of profiles/r2e), 0 = register-tiled fp32 FMA kernel
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
   int conv3x3_dual = 1;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass (default: -2.3 % step
                           // time in the same-box A/B of profiles/r2d_variants_ab.md)
@@ -1260,7 +1276,7 @@ static void drop_plans(film_handle* h) {
 static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   char key[96];
   snprintf(key, sizeof(key), "%dx%d_a%d_i%d_v%d_l%d_p%d_h%d_m%x_d%d", hh, ww, align > 0 ? align : 0, h->conv_impl, h->conv3x3_v2,
-           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 128 + h->fuse_flow_head * 64 + h->arena_reuse * 32 + h->mma_straight * 16 + h->plane_skip * 8 + h->conv3x3_dual * 4 +
+           h->use_lanes, h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->keep_debug * 256 + h->fuse_flow_head * 64 + h->arena_reuse * 32 + h->mma_straight * 16 + h->plane_skip * 8 + h->conv3x3_dual * 4 +
                h->fuse_rgb_head * 2 + h->fe_conv0_tc);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
@@ -1268,7 +1284,8 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
   try {
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
                    h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
-                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64));
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64) |
+                       (h->fuse_flow_head >= 2 ? 128 : 0));
   } catch (const Error& e0) {
     if (e0.code != FILM_ERR_CUDA) throw;  // only an allocation failure is worth a retry
     // Every cached shape keeps its activation arena (GBs at 1080p).  If a new shape does not fit next to
@@ -1277,7 +1294,8 @@ static Plan* get_plan(film_handle* h, int hh, int ww, int align) {
     drop_plans(h);
     p = build_plan(*h->model, hh, ww, align, h->conv_impl, h->keep_debug != 0, h->conv3x3_v2, h->num_sms,
                    h->conv3x3_2cta, h->conv3x3_halo, h->onepass_mask, h->use_lanes != 0, h->fe_conv0_tc | (h->fuse_rgb_head ? 0 : 2) | (h->conv3x3_dual ? 4 : 0) | (h->plane_skip ? 0 : 8) |
-                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64));
+                       (h->mma_straight ? 0 : 16) | (h->arena_reuse ? 0 : 32) | (h->fuse_flow_head ? 0 : 64) |
+                       (h->fuse_flow_head >= 2 ? 128 : 0));
   }
   if (h->use_graph) {
     cudaGraph_t g = nullptr;
@@ -1366,7 +1384,7 @@ int film_create(film_handle** out, const char* weights_path, int device_ordinal)
     if (const char* e6 = getenv("FILM_RGB_FUSE")) h->fuse_rgb_head = atoi(e6) ? 1 : 0;
     if (const char* e7 = getenv("FILM_DUAL")) h->conv3x3_dual = atoi(e7) ? 1 : 0;
     if (const char* e8 = getenv("FILM_PLANE_SKIP")) h->plane_skip = atoi(e8) ? 1 : 0;
-    if (const char* e11 = getenv("FILM_FLOW_HEAD_FUSE")) h->fuse_flow_head = atoi(e11) ? 1 : 0;
+    if (const char* e11 = getenv("FILM_FLOW_HEAD_FUSE")) h->fuse_flow_head = atoi(e11) < 0 ? 0 : (atoi(e11) > 2 ? 2 : atoi(e11));
     if (const char* e9 = getenv("FILM_STRAIGHT")) h->mma_straight = atoi(e9) ? 1 : 0;
     if (const char* e10 = getenv("FILM_ARENA_REUSE")) h->arena_reuse = atoi(e10) ? 1 : 0;
     if (const char* e4 = getenv("FILM_ONEPASS")) h->onepass_mask = (uint32_t)strtoul(e4, nullptr, 0);
@@ -1436,7 +1454,7 @@ int film_set_option(film_handle* h, const char* name, int value) {
   else if (n == "fuse_rgb_head") h->fuse_rgb_head = value ? 1 : 0;
   else if (n == "conv3x3_dual") h->conv3x3_dual = value ? 1 : 0;
   else if (n == "plane_skip") h->plane_skip = value ? 1 : 0;
-  else if (n == "fuse_flow_head") h->fuse_flow_head = value ? 1 : 0;
+  else if (n == "fuse_flow_head") h->fuse_flow_head = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (n == "mma_straight") h->mma_straight = value ? 1 : 0;
   else if (n == "arena_reuse") h->arena_reuse = value ? 1 : 0;
   else if (n == "clear_plans") drop_plans(h);

@@ -149,8 +149,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   (UMMA descriptors at pixel offsets): 3 = both persistent kernels, 64- and 32-channel chunks
  *                   (default: validated on hardware in round 2, -0.6 % / -2.0 % step time in two same-box A/Bs),
  *                   2 = 64-channel chunks only, 1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
- *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image
- *                   (default), 1 = tensor-core kernel over a 32-channel-padded split image (comparison)
+ *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 1 = tensor-core kernel over a 32-channel-padded split image (default:
+ *                   measured faster, 0.78 ms against 0.87 ms over the seven levels), 0 = register-tiled fp32 FMA kernel
+ *                   reading the fp32 image directly (exact fp32 arithmetic, no widened image tensor)
  *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes
  *                   resident, two accumulator sets in TMEM): halves the weight bytes pulled from L2 per item on the
  *                   layers that are L2->SM ingest bound (default); 0 = one item per weight pass
@@ -159,8 +160,8 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *   "mma_straight": 1 = with resident weights one elected lane issues a whole activation stage as straight-line code
  *                   (default), 0 = per-tap issue loop
  *   "arena_reuse" : 1 = activation buffers are recycled inside a plan by liveness (default), 0 = one buffer per tensor
- *   "fuse_flow_head": 1 = on the flow levels whose predictor has <= 64 filters (levels 0 and 1) conv_3, conv_4 and the
- *                   residual add run in the epilogue of conv_2 (default), 0 = separate head launch
+ *   "fuse_flow_head": 1 = on flow level 0 (32-filter predictor) conv_3, conv_4 and the residual add run in the epilogue of
+ *                   conv_2 (default), 2 = also on level 1 (64 filters: measured epilogue-bound, slower), 0 = separate launch
  *   "fuse_rgb_head": 1 = the linear 1x1 RGB head and the crop run in the epilogue of the decoder's last 3x3 conv (default;
  *                   the 64-channel activation is never stored), 0 = separate kernel
  *   "use_lanes"   : 1 = enqueue independent branches on separate streams (default 0)
