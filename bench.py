@@ -87,7 +87,11 @@ class ClockSampler:
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
-            time.sleep(0.15)     # let the first samples arrive before the timed region starts
+            # nvidia-smi can take seconds to start on a fresh box: do not open the timed region before the first
+            # sample has arrived, or a 0.3 s region ends with no clock record at all
+            t_end = time.time() + 8.0
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self._proc = None
         return self

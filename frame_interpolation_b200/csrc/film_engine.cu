@@ -1200,8 +1200,10 @@ struct film_handle {
                          // persistent kernels, 3 also the 32-channel-chunk layers (default: validated on hardware in
                          // round 2, -0.6 % / -2.0 % step time in two same-box A/Bs, profiles/r2c|r2d_variants_ab.md)
   uint32_t onepass_mask = kDefaultOnepassMask;  // precision plan (see `enum Stage`)
-  int fe_conv0_tc = 1;  // cfeat_conv_0: 1 = tensor-core kernel over the 32-channel-padded image (default: 0.78 ms over
-                        // the 7 levels against 0.87 ms, per-op timing of profiles/r2e), 0 = register-tiled fp32 FMA kernel
+  int fe_conv0_tc = 0;  // cfeat_conv_0: 0 = register-tiled fp32 FMA kernel straight from the fp32 image (default: exact fp32,
+                        // no widened image tensor; K = 27 is not tensor-core work), 1 = tensor-core kernel over the
+                        // 32-channel-padded image (per-op timing of profiles/r2e: 0.78 ms over the 7 levels against 0.87 ms,
+                        // i.e. 0.6 % of the step -- inside the run-to-run noise of the whole-step A/B)
   int fuse_rgb_head = 1;  // 1 = RGB head + crop in the epilogue of fusion_conv2@L0 (default), 0 = separate kernel
   int conv3x3_dual = 1;   // 1 = CTA-pair kernel serves two spatial items per streamed weight pass (default: -2.3 % step
                           // time in the same-box A/B of profiles/r2d_variants_ab.md)

@@ -149,9 +149,9 @@ FILM_API int film_profile(film_handle* h, film_profile_t* out);
  *                   (UMMA descriptors at pixel offsets): 3 = both persistent kernels, 64- and 32-channel chunks
  *                   (default: validated on hardware in round 2, -0.6 % / -2.0 % step time in two same-box A/Bs),
  *                   2 = 64-channel chunks only, 1 = CTA-pair kernel only, 0 = three dx-shifted 8-px boxes
- *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 1 = tensor-core kernel over a 32-channel-padded split image (default:
- *                   measured faster, 0.78 ms against 0.87 ms over the seven levels), 0 = register-tiled fp32 FMA kernel
- *                   reading the fp32 image directly (exact fp32 arithmetic, no widened image tensor)
+ *   "fe_conv0_tc" : cfeat_conv_0 (3 -> 64, K = 27): 0 = register-tiled fp32 FMA kernel reading the fp32 image directly
+ *                   (default: exact fp32 arithmetic, no widened image tensor), 1 = tensor-core kernel over a 32-channel-
+ *                   padded split image (0.78 ms against 0.87 ms over the seven levels in per-op timing)
  *   "conv3x3_dual": 1 = the CTA-pair kernel serves TWO spatial work items per streamed weight tap (both items' halo boxes
  *                   resident, two accumulator sets in TMEM): halves the weight bytes pulled from L2 per item on the
  *                   layers that are L2->SM ingest bound (default); 0 = one item per weight pass

@@ -293,7 +293,7 @@ def test_cli_end_to_end(tmp_path, synthetic_weights):
 
 @pytest.mark.parametrize("option,value", [("conv3x3_2cta", 0), ("conv3x3_2cta", 2), ("conv3x3_v2", 0),
                                           ("conv3x3_halo", 0), ("conv3x3_halo", 1), ("conv3x3_halo", 2), ("conv3x3_halo", 3),
-                                          ("fe_conv0_tc", 0), ("fuse_rgb_head", 0), ("conv3x3_dual", 0),
+                                          ("fe_conv0_tc", 1), ("fuse_rgb_head", 0), ("conv3x3_dual", 0),
                                           ("mma_straight", 0), ("plane_skip", 0), ("arena_reuse", 0), ("fuse_flow_head", 0), ("fuse_flow_head", 2)])
 def test_kernel_variants_agree(synthetic_weights, oracle, option, value):
     """Every conv kernel variant (generic, persistent, CTA-pair on all eligible layers, wide-halo boxes off /

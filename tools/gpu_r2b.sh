@@ -9,7 +9,7 @@ source gpurun_out/good_env.sh
 cat gpurun_out/good_env.sh
 timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
 tail -25 gpurun_out/${T}_pytest.log
-for cfg in "default" "FILM_HALO=2" "FILM_HALO=0" "FILM_2CTA=2" "FILM_2CTA=0" "FILM_FE0_TC=0" "FILM_RGB_FUSE=0" "FILM_DUAL=0" "FILM_STRAIGHT=0" "FILM_PLANE_SKIP=0" "FILM_ARENA_REUSE=0" "FILM_FLOW_HEAD_FUSE=0" "FILM_FLOW_HEAD_FUSE=2"; do
+for cfg in "default" "FILM_HALO=2" "FILM_HALO=0" "FILM_2CTA=2" "FILM_2CTA=0" "FILM_FE0_TC=1" "FILM_RGB_FUSE=0" "FILM_DUAL=0" "FILM_STRAIGHT=0" "FILM_PLANE_SKIP=0" "FILM_ARENA_REUSE=0" "FILM_FLOW_HEAD_FUSE=0" "FILM_FLOW_HEAD_FUSE=2"; do
   name=$(echo $cfg | tr '=' '_')
   if [ "$cfg" = "default" ]; then envs=""; else envs="$cfg"; fi
   env $envs timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-workloads --op-table gpurun_out/${T}_ops_$name.csv > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
