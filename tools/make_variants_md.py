@@ -1,4 +1,4 @@
-"""profiles/<tag>_variants_ab.md from the same-box A/B bench runs of tools/gpu_r2b.sh (gpurun_out/<tag>_bench_<cfg>.json)."""
+"""profiles/<tag>_variants_ab.md from the same-box A/B bench runs of tools/gpu_full_r2.sh (gpurun_out/<tag>_bench_<cfg>.json)."""
 import glob, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
