@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
   int nkb = 0;                                                  // K blocks = (source, chunk, dx, dy)
   for (int s = 0; s < nsrc; ++s) nkb += prob->src[s].nchunk * 9;
 
+  const FastDiv div_nt(n_nt, ntiles), div_img(tiles_per_img, ntiles), div_tx(tiles_x, ntiles);   // tile decode
+
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - raw);
@@ -150,15 +152,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     __syncwarp();
     RingPos ra, rw;   // activation / weight ring positions
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int sp = tile / n_nt, n0 = (tile % n_nt) * BN;
-      const int b = sp / tiles_per_img, rem = sp % tiles_per_img;
-      const int y0 = (rem / tiles_x) * kTileH, x0 = (rem % tiles_x) * kTileW;
+      int sp, nti, b, rem, ty, tx;
+      div_nt.divmod(tile, sp, nti);
+      div_img.divmod(sp, b, rem);
+      div_tx.divmod(rem, ty, tx);
+      const int n0 = nti * BN, y0 = ty * kTileH, x0 = tx * kTileW;
       {
         // L2 prefetch of this CTA's NEXT spatial tile: first touch of an activation tile is DRAM
         const int nt = tile + gridDim.x;
-        if (nt < ntiles && nt / n_nt != sp && elect_one()) {
-          const int nsp = nt / n_nt, nb = nsp / tiles_per_img, nrem = nsp % tiles_per_img;
-          const int ny0 = (nrem / tiles_x) * kTileH, nx0 = (nrem % tiles_x) * kTileW;
+        int nsp, nnt;
+        div_nt.divmod(nt < ntiles ? nt : 0, nsp, nnt);
+        if (nt < ntiles && nsp != sp && elect_one()) {
+          int nb, nrem, nty, ntx;
+          div_img.divmod(nsp, nb, nrem);
+          div_tx.divmod(nrem, nty, ntx);
+          const int ny0 = nty * kTileH, nx0 = ntx * kTileW;
           for (int s = 0; s < nsrc; ++s)
             for (int ch = 0; ch < src_tab[2 * s]; ++ch) {
               // the three dx boxes overlap: boxes at dx = 0 and dx = 2 cover the (tile_w + 2)-px-wide halo
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // which 16-column chunks (even / odd) this warp drains
     const int r = q * 32 + lane;
+    const int r_y = r / kTileW, r_x = r % kTileW;   // position of this thread's pixel inside the tile (tile-invariant)
     const int H = prob->H, W = prob->W, out_H = prob->out_H, out_W = prob->out_W, out_C = prob->out_C;
     const int out_c_off = prob->out_c_off, act = prob->act;
     sp_t* const out_hi = prob->out_hi;
@@ -413,9 +422,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(const ConvProblem* _
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
-      const int sp = tile / n_nt, n0 = (tile % n_nt) * BN;
-      const int b = sp / tiles_per_img, rem = sp % tiles_per_img;
-      const int py = (rem / tiles_x) * kTileH + r / kTileW, px = (rem % tiles_x) * kTileW + r % kTileW;
+      int sp, nti, b, rem, ty, tx;
+      div_nt.divmod(tile, sp, nti);
+      div_img.divmod(sp, b, rem);
+      div_tx.divmod(rem, ty, tx);
+      const int n0 = nti * BN;
+      const int py = ty * kTileH + r_y, px = tx * kTileW + r_x;
       const bool valid = (py < H) && (px < W);
       const int64_t opix = ((int64_t)b * out_H + py) * out_W + px;
       sp_t* oh = out_hi + opix * out_C + out_c_off + n0;

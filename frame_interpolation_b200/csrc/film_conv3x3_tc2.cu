@@ -104,6 +104,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   int nkb = 0;
   for (int s = 0; s < nsrc; ++s) nkb += prob->src[s].nchunk * 9;
 
+  const FastDiv div_nt(n_nt, nitems), div_img(pairs_per_img, nitems), div_tx(tiles_x, nitems);   // item decode
+
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - raw);
@@ -192,8 +194,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           for (int ch = 0; ch < nchunk; ++ch) {
             for (int sub = 0; sub < nsub; ++sub) {
               const int sp = 2 * sit + sub;   // n_nt == 1
-              const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
-              const int y0 = (2 * (rem / tiles_x) + (int)rank) * kTileH, x0 = (rem % tiles_x) * kTileW;
+              int b, rem, ty, tx;
+              div_img.divmod(sp, b, rem);
+              div_tx.divmod(rem, ty, tx);
+              const int y0 = (2 * ty + (int)rank) * kTileH, x0 = tx * kTileW;
               const int bs = swap ? prob->B - 1 - b : b;
               const int st = ra.stage;
               mbar_wait(a_empty(st), ra.phase ^ 1u);
@@ -232,9 +236,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     } else {
     for (int item = item0; item < nitems; item += item_step) {
-      const int sp = item / n_nt, n0 = (item % n_nt) * BN;
-      const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
-      const int y0 = (2 * (rem / tiles_x) + (int)rank) * kTileH, x0 = (rem % tiles_x) * kTileW;
+      int sp, nti, b, rem, ty, tx;
+      div_nt.divmod(item, sp, nti);
+      div_img.divmod(sp, b, rem);
+      div_tx.divmod(rem, ty, tx);
+      const int n0 = nti * BN;
+      const int y0 = (2 * ty + (int)rank) * kTileH, x0 = tx * kTileW;
       int kb = 0;
       for (int s = 0; s < nsrc; ++s) {
         const int nchunk = src_tab[2 * s], c_off = src_tab[2 * s + 1];
@@ -570,9 +577,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int nsub = (dual && 2 * sit + 1 < nitems) ? 2 : 1;
      for (int sub = 0; sub < nsub; ++sub) {
       const int item = dual ? 2 * sit + sub : sit;
-      const int sp = item / n_nt, n0 = (item % n_nt) * BN;
-      const int b = sp / pairs_per_img, rem = sp % pairs_per_img;
-      const int py = (2 * (rem / tiles_x) + (int)rank) * kTileH + r / kTileW, px = (rem % tiles_x) * kTileW + r % kTileW;
+      int sp, nti, b, rem, ty, tx;
+      div_nt.divmod(item, sp, nti);
+      div_img.divmod(sp, b, rem);
+      div_tx.divmod(rem, ty, tx);
+      const int n0 = nti * BN;
+      const int py = (2 * ty + (int)rank) * kTileH + r / kTileW, px = tx * kTileW + r % kTileW;
       const bool valid = (py < H) && (px < W);
       const int64_t opix = ((int64_t)b * out_H + py) * out_W + px;
       sp_t* oh = out_hi + opix * out_C + out_c_off + n0;

@@ -106,6 +106,25 @@ struct RingPos {
   }
 };
 
+// Division by a kernel-invariant divisor without the ~25-instruction I2F / MUFU.RCP / IABS sequence of a runtime `/`:
+// q = (x * ceil(2^40 / d)) >> 40 is exact whenever x * d < 2^40 (tile indices and tile counts are < 2^20 for every frame
+// this engine accepts); otherwise the plain division is used.  The per-tile decode tile -> (b, y0, x0) runs in every
+// producer and epilogue warp for every tile (source-level ncu, profiles/r2i_stalls_flow_L0.md).
+struct FastDiv {
+  uint64_t mul;
+  uint32_t d;
+  bool fast;
+  __device__ __forceinline__ FastDiv(int divisor, int max_x) : d((uint32_t)divisor) {
+    fast = (uint64_t)(uint32_t)max_x * d < (1ull << 40);
+    mul = ((1ull << 40) + d - 1) / d;
+  }
+  __device__ __forceinline__ void divmod(int x, int& q, int& r) const {
+    const uint32_t qq = fast ? (uint32_t)(((uint64_t)(uint32_t)x * mul) >> 40) : (uint32_t)x / d;
+    q = (int)qq;
+    r = x - (int)(qq * d);
+  }
+};
+
 // K-major swizzled descriptor with an explicit stride between 8-row groups.  The hardware applies the
 // swizzle XOR on ABSOLUTE smem address bits (7..9 -> 4..6; 7..8 -> 4..5 for SWIZZLE_64B) and base_offset stays
 // 0: measured on B200 with tools/ubench/desc_offset_test.cu -- the start address may sit at any row inside
