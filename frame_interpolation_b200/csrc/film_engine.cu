@@ -799,7 +799,10 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
       return launch_pad_image(src, (int64_t)pp->w * 3, pp->h, pp->w, dst, pp->H, pp->W, pp->off_y, pp->off_x, st);
     });
   }
-  for (int l = 0; l + 1 < kLevels; ++l) {
+  // image pyramid (util.py:38-44): fused into the first conv of each scale when that conv is the FMA kernel (it has the
+  // input patch in shared memory anyway); stand-alone pools otherwise (tensor-core first layer, validation path, lanes)
+  const bool fuse_img_pool = P.conv_impl == 0 && !P.fe_conv0_tc && !use_lanes;
+  for (int l = 0; l + 1 < kLevels && !fuse_img_pool; ++l) {
     const float* in = img[l];
     float* out = img[l + 1];
     const int hh = Hs[l], ww = Ws[l];
@@ -829,8 +832,9 @@ static std::unique_ptr<Plan> build_plan(const Model& M, int h, int w, int align,
         const float *w0 = M.conv0_w, *b0 = M.conv0_b;
         sp_t *oh = t1->hi, *ol = t1->lo;
         const bool lo_skip = P.plane_skip && ((P.onepass_mask >> fe_stage(i, 1)) & 1u);   // only reader: cfeat_conv_1 of this sub-tree
-        P.add_op(2, "fe_conv0@L" + std::to_string(r),
-                 [=](cudaStream_t st) { return launch_fe_conv0(im, 2, hh, ww, w0, b0, oh, ol, lo_skip, st); },
+        float* pool_dst = (fuse_img_pool && i + 1 < kLevels) ? img[i + 1] : nullptr;   // next pyramid level
+        P.add_op(2, std::string(pool_dst ? "fe_conv0+pool@L" : "fe_conv0@L") + std::to_string(r),
+                 [=](cudaStream_t st) { return launch_fe_conv0(im, 2, hh, ww, w0, b0, oh, ol, lo_skip, pool_dst, st); },
                  2.0 * 27 * 64 * 2.0 * hh * ww, 2.0 * hh * ww * (3 * 4 + 64 * (lo_skip ? 2.0 : 4.0)));
       } else if (j == 0 && P.conv_impl == 0 && P.conv3x3_v2) {
         // cfeat_conv_0 on the persistent 3x3 tensor-core kernel: the image is widened to a 32-channel

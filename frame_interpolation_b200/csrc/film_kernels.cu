@@ -189,7 +189,8 @@ __device__ __forceinline__ float fe_patch_load(const float* __restrict__ img, in
 }
 __global__ void __launch_bounds__(128) k_fe_conv0(const float* __restrict__ img, int H, int W,
                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                  sp_t* __restrict__ out_hi, sp_t* __restrict__ out_lo, int lo_skip) {
+                                                  sp_t* __restrict__ out_hi, sp_t* __restrict__ out_lo, int lo_skip,
+                                                  float* __restrict__ pool_out) {
   __shared__ float4 ws[27 * 16];                            // [tap * 3 + ci][64 channels]
   __shared__ float bs[64];
   __shared__ float patch[kC0Patch];                         // zero outside the image == SAME padding
@@ -212,6 +213,18 @@ __global__ void __launch_bounds__(128) k_fe_conv0(const float* __restrict__ img,
     for (int j = 0; j < kC0PatchRegs; ++j)
       if (tid + 128 * j < kC0Patch) patch[tid + 128 * j] = nxt[j];
     __syncthreads();
+    // util.py:38-44 fused: the 2x2/2 average pool of this image level (= the next pyramid level, the input of the
+    // same conv one scale up) is taken from the patch that is already in shared memory; same summation order as
+    // k_image_pool, so the pyramid is bit-identical to the stand-alone kernel's
+    if (pool_out != nullptr && tid < (kC0H / 2) * (kC0W / 2) * 3) {
+      const int c = tid % 3, qx = (tid / 3) % (kC0W / 2), qy = tid / (3 * (kC0W / 2));
+      const int oy = (y0 >> 1) + qy, ox = (x0 >> 1) + qx;
+      if (oy < (H >> 1) && ox < (W >> 1)) {
+        const float* p0 = patch + ((2 * qy + 1) * (kC0W + 2) + 2 * qx + 1) * 3 + c;
+        const float* p1 = p0 + (kC0W + 2) * 3;
+        pool_out[(((int64_t)b * (H >> 1) + oy) * (W >> 1) + ox) * 3 + c] = (p0[0] + p0[3] + p1[0] + p1[3]) * 0.25f;
+      }
+    }
     if (tile + 1 < kC0Tiles && x0 + kC0W < W) {             // prefetch the next tile's patch (latency hidden by the FMAs)
 #pragma unroll
       for (int j = 0; j < kC0PatchRegs; ++j) nxt[j] = fe_patch_load(img, b, H, W, y0, x0 + kC0W, tid + 128 * j);
@@ -259,9 +272,9 @@ __global__ void __launch_bounds__(128) k_fe_conv0(const float* __restrict__ img,
   }
 }
 cudaError_t launch_fe_conv0(const float* img, int B, int H, int W, const float* w, const float* bias, sp_t* out_hi,
-                            sp_t* out_lo, bool lo_skip, cudaStream_t st) {
+                            sp_t* out_lo, bool lo_skip, float* pool_out, cudaStream_t st) {
   dim3 grid((W + kC0W * kC0Tiles - 1) / (kC0W * kC0Tiles), (H + kC0H - 1) / kC0H, B);
-  k_fe_conv0<<<grid, 128, 0, st>>>(img, H, W, w, bias, out_hi, out_lo, lo_skip ? 1 : 0);
+  k_fe_conv0<<<grid, 128, 0, st>>>(img, H, W, w, bias, out_hi, out_lo, lo_skip ? 1 : 0, pool_out);
   return cudaGetLastError();
 }
 

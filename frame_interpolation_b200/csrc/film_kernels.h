@@ -17,8 +17,10 @@ cudaError_t launch_conv0_c3(const float* img, int B, int H, int W, const float* 
 
 // Product path of cfeat_conv_0: register-tiled fp32 direct conv (K = 27 is too short for the tensor cores), reads the
 // fp32 image level, writes the 64-channel split output [B][H][W][64] (hi plane only when `lo_skip`).
+// `pool_out` (nullable): [B][H/2][W/2][3] fp32 -- the 2x2/2 average pool of `img` (util.py:38-44), i.e. the next image
+// pyramid level, written from the input patch the conv has staged anyway (H, W even).
 cudaError_t launch_fe_conv0(const float* img, int B, int H, int W, const float* w, const float* bias, sp_t* out_hi,
-                            sp_t* out_lo, bool lo_skip, cudaStream_t st);
+                            sp_t* out_lo, bool lo_skip, float* pool_out, cudaStream_t st);
 
 // im2col-lite for the tensor-core version of cfeat_conv_0: [B][H][W][3] fp32 -> [B][H][W][32] split
 // (27 tap x channel values in HWIO order + 5 zero channels, zero outside the image).
