@@ -67,3 +67,16 @@ def test_recursion_yields_2_pow_n_plus_1_frames_in_time_order(n):
     assert len(frames) == 2 ** n + 1
     for k, f in enumerate(frames):
         np.testing.assert_allclose(f, k / 2 ** n, atol=1e-6)
+
+
+@given(st.integers(min_value=1, max_value=1 << 19), st.integers(min_value=0, max_value=(1 << 21) - 1))
+@settings(max_examples=400, deadline=None)
+def test_multiply_shift_tile_decode_is_exact(d, x):
+    """The device-side tile decode (csrc/film_tc_ptx.cuh `FastDiv`) replaces `x / d` by (x * ceil(2^40 / d)) >> 40 when
+    x * d < 2^40 and falls back to the plain division otherwise; the multiply-shift form must be exact on its domain
+    (tile indices / tile counts of every frame the engine accepts are far inside it)."""
+    if x * d >= 1 << 40:
+        return
+    mul = ((1 << 40) + d - 1) // d
+    q = (x * mul) >> 40
+    assert q == x // d and x - q * d == x % d
