@@ -252,8 +252,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster (the peer's epilogue warps hand the accumulator back to the leader's MMA
+// warp).  Default semantics (.release at CTA scope), like CUTLASS's ClusterBarrier::arrive(cta_id): what the waiter depends on
+// is the completion of this warp's tcgen05.ld (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede the arrive), not
+// the visibility of its global stores.  The former `.release.cluster` form compiled to MEMBAR.ALL.GPU + ERRBAR in front of
+// every arrive: each epilogue warp waited for its output stores to become GPU-visible once per tile -- 34 % of all stall
+// samples of flow_conv0@L0 (source-level ncu, profiles/r2i_stalls_flow_L0.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0,
                                                 int c1, int c2, int c3) {
