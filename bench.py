@@ -128,8 +128,8 @@ class ClockSampler:
 _BEST_THREADS = None
 REF_WALL_BUDGET_S = 200.0      # the reference arm must end "within a few minutes"
 # DRAM bytes (read + write) of the tensor-core conv launches of ONE 1080p call, summed from the committed ncu capture
-# profiles/r2j_ncu_counters_1080p.csv (tools/gpu_final_r2.sh: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,...`)
-NCU_CONV_DRAM_BYTES_PER_STEP = 20.184e9
+# profiles/r2l_ncu_counters_1080p.csv (tools/gpu_final_r2.sh: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,...`)
+NCU_CONV_DRAM_BYTES_PER_STEP = 20.209e9
 
 
 def _pick_threads():
@@ -494,8 +494,8 @@ def main():
         "achieved": ach_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": ach_tf / peaks["bf16_tflops_sustained"], "traffic": NCU_CONV_DRAM_BYTES_PER_STEP,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 76 tensor-core conv launches of one 1080p "
-                        "call, ncu capture of build r2j (profiles/r2j_ncu_counters_1080p.csv; dominant launch fusion_conv1@L1: "
-                        "1.55 GB in 1.24 ms, tensor pipe 79 %; conv launches = 82.9 % of the step under ncu, 82.1 % by CUDA events); `algorithmic_bytes_per_step` is the engine's own count (every "
+                        "call, ncu capture of build r2l (profiles/r2l_ncu_counters_1080p.csv; dominant launch fusion_conv1@L1: "
+                        "1.55 GB in 1.24 ms, tensor pipe 79 %; conv launches = 82.8 % of the step under ncu, 82.0 % by CUDA events); `algorithmic_bytes_per_step` is the engine's own count (every "
                         "source plane a call site consumes read once, every destination plane written once)",
         "algorithmic_bytes_per_step": sum(a["alg_bytes"] for a in conv),
         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
