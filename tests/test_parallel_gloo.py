@@ -108,9 +108,11 @@ def test_single_process_paths_match_serial():
     assert v.shape == (4, 6, 3) and v.stride(0) == 18 * 3 and v.data_ptr() == t0[0, 4, 6].data_ptr()
 
 
-@pytest.mark.timeout(180)
-def test_world_size_2_gloo_bitwise_equals_serial():
-    world = 2
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("world", [2, 3])
+def test_world_size_n_gloo_bitwise_equals_serial(world):
+    """world 3 exercises the uneven shares: 5 pairs -> 2/2/1, 9 tiles -> 3/3/3, 16 tiles -> 6/5/5, recursion levels of 1/2/4
+    calls over 3 ranks (ranks with nothing to do still take part in the in-place all-gather)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -134,6 +136,7 @@ def test_world_size_2_gloo_bitwise_equals_serial():
         np.testing.assert_array_equal(got[r]["tiled_dev"], tiled)
         np.testing.assert_array_equal(got[r]["rec_dev"], seq)
         np.testing.assert_array_equal(got[r]["tiled_dev_4x4"], tiled44)
-    # local shares: rank 0 gets pairs [0,3), rank 1 gets [3,5)
-    np.testing.assert_array_equal(got[0]["pairs_local"], pairs[:3])
-    np.testing.assert_array_equal(got[1]["pairs_local"], pairs[3:])
+    # local shares are the contiguous block partition
+    for r in range(world):
+        lo, hi = parallel.block_partition(5, world, r)
+        np.testing.assert_array_equal(got[r]["pairs_local"], pairs[lo:hi])
